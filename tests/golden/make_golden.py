@@ -1,0 +1,133 @@
+"""Generate the golden fixtures in tests/golden/*.pt from the UNMODIFIED reference.
+
+Build-container only: imports /root/reference through oracle/ref_shim.py.  The fixtures hold inputs
+and the reference's outputs (and intermediate taps); the WEIGHTS are not stored — they are regenerated
+anywhere from `oracle.gcpnet_oracle.random_state_dict(cfg, seed)` (torch CPU generator, deterministic)
+and were loaded into the reference module with `load_state_dict(strict=True)` before it was run.  A
+checksum of the weights is stored so a drift of the generator is caught before any comparison.
+
+Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+import warnings
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+warnings.filterwarnings("ignore")
+import ref_shim  # noqa: E402
+import gcpnet_oracle as O  # noqa: E402
+
+WEIGHT_SEED = 7
+
+
+def weight_checksum(sd):
+    tot = sum(float(v.double().sum()) for v in sd.values())
+    sq = sum(float((v.double() ** 2).sum()) for v in sd.values())
+    return torch.tensor([tot, sq], dtype=torch.float64)
+
+
+def make_inputs(cfg, sizes, seed, mask_mode="none"):
+    g = torch.Generator().manual_seed(seed)
+    B = len(sizes)
+    bi = torch.repeat_interleave(torch.arange(B), torch.tensor(sizes))
+    N = bi.shape[0]
+    mask = torch.ones(N, dtype=torch.bool)
+    if mask_mode == "pad":   # suffix padding on even molecules + one interior hole
+        off = 0
+        for k, n in enumerate(sizes):
+            if k % 2 == 0 and n > 3:
+                mask[off + n - 2: off + n] = False
+            off += n
+        mask[1] = False
+    xh = torch.randn((N, 3 + cfg.num_h), generator=g) * mask[:, None]
+    _, xc = O.centralize(xh[:, :3], bi, mask, B)
+    xh = torch.cat((xc, xh[:, 3:]), -1)
+    t = torch.rand((B, 1), generator=g)[bi].contiguous()
+    ctx = (torch.randn((B, cfg.num_context), generator=g)[bi] * mask[:, None]) if cfg.num_context else None
+    return bi, mask, xh, t, ctx
+
+
+def reference_with_weights(cname):
+    net, _ = ref_shim.build_reference_dynamics(cname, seed=0)
+    cfg = O.config_named(cname)
+    sd = O.random_state_dict(cfg, WEIGHT_SEED)
+    net.load_state_dict(sd, strict=True)
+    return net, cfg, sd
+
+
+def forward_case(cname, sizes, seed, mask_mode="none", layer_taps=False):
+    net, cfg, sd = reference_with_weights(cname)
+    bi, mask, xh, t, ctx = make_inputs(cfg, sizes, seed, mask_mode)
+    batch = ref_shim.Batch(batch=bi, mask=mask, props_context=ctx)
+    taps = []
+    hooks = []
+    if layer_taps:
+        for layer in net.interaction_layers:
+            hooks.append(layer.register_forward_hook(
+                lambda m, i, o: taps.append(dict(h=o[0][0].clone(), chi=o[0][1].clone(), x=o[1].clone()))))
+    with torch.no_grad():
+        _, out = net(batch, xh.clone(), t)
+    for h in hooks:
+        h.remove()
+    fx = dict(config=cname, sizes=list(sizes), weight_seed=WEIGHT_SEED, weight_checksum=weight_checksum(sd),
+              batch_index=bi, mask=mask, xh=xh, t=t, context=ctx, net_out=out.clone(),
+              num_edges=int(batch.edge_index.shape[1]))
+    if layer_taps:
+        fx.update(edge_index=batch.edge_index.clone(), f_ij=batch.f_ij.clone(), e=batch.e.clone(),
+                  xi=batch.xi.clone(), x_final=batch.x.clone(), chi_final=batch.chi.clone(), layers=taps)
+    return fx
+
+
+def chain_case(cname, sizes, steps, seed):
+    ddpm, _ = ref_shim.build_reference_ddpm(cname, seed=0)
+    cfg = O.config_named(cname)
+    sd = O.random_state_dict(cfg, WEIGHT_SEED)
+    ddpm.dynamics_network.load_state_dict(sd, strict=True)
+    zs = []
+    hook = ddpm.dynamics_network.register_forward_pre_hook(lambda m, args: zs.append(args[1].clone()))
+    num_nodes = torch.tensor(sizes)
+    ctx = None
+    if cfg.num_context:
+        ctx = torch.randn((len(sizes), cfg.num_context), generator=torch.Generator().manual_seed(seed + 1))
+    torch.manual_seed(seed)
+    out, bi, mask = ddpm.mol_gen_sample(num_samples=len(sizes), num_nodes=num_nodes, device="cpu",
+                                        num_timesteps=steps, context=ctx)
+    hook.remove()
+    return dict(config=cname, sizes=list(sizes), steps=steps, noise_seed=seed, weight_seed=WEIGHT_SEED,
+                weight_checksum=weight_checksum(sd), context=ctx, out=out.clone(), z_T=zs[0], z_1=zs[1],
+                z_0=zs[-1], gamma=ddpm.gamma.gamma.data.clone())
+
+
+def main():
+    fixtures = {
+        # integer KAT for the edge index, observed from the reference
+        "kat_edge_index": None,
+        "qm9_small_masked": forward_case("qm9", [5, 9, 3, 7], 11, "pad", layer_taps=True),
+        "qm9_tiny_sizes": forward_case("qm9", [1, 2, 3, 1], 12),
+        "qm9_b4_n19": forward_case("qm9", [19, 19, 19, 19], 13),
+        "qm9_cond": forward_case("qm9_cond", [19, 12, 23], 14),
+        "geom_mixed": forward_case("geom", [44, 30, 61, 25], 15),
+        "geom_max181": forward_case("geom", [181, 3], 16),
+        "chain_qm9_T6": chain_case("qm9", [19, 7, 12], 6, 123),
+        "chain_qm9_cond_T4": chain_case("qm9_cond", [9, 14], 4, 321),
+        "chain_geom_T3": chain_case("geom", [30, 44], 3, 77),
+    }
+    from src.models.components.gcpnet import GCPNetDynamics
+    bi = torch.tensor([0] * 5 + [1] * 5)
+    mk = torch.tensor([1, 1, 1, 0, 0, 1, 1, 1, 1, 0], dtype=torch.bool)
+    fixtures["kat_edge_index"] = dict(
+        batch_index=bi, mask=mk,
+        edge_index=GCPNetDynamics.get_fully_connected_edge_index(bi, mk),
+        edge_index_nomask=GCPNetDynamics.get_fully_connected_edge_index(bi, None))
+    for name, fx in fixtures.items():
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(fx, path)
+        print(f"{name:22s} {os.path.getsize(path) / 1024:8.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,97 @@
+"""CPU: the oracle restatement reproduces the reference outputs stored in tests/golden/.
+
+The fixtures were produced by the unmodified reference (tests/golden/make_golden.py); the weights are
+regenerated from their seed and checksummed first.  Tolerances: integer work bit-exact; floating
+point max-abs <= 2e-5 * max(1, |ref|_max) per forward (the measured fp32-vs-fp64 floor is ~1e-6,
+SURVEY.md §8c), chains 1e-3 relative.
+"""
+import pytest
+import torch
+
+import gcpnet_oracle as O
+from conftest import load_golden
+
+FWD_CASES = ["qm9_small_masked", "qm9_tiny_sizes", "qm9_b4_n19", "qm9_cond", "geom_mixed", "geom_max181"]
+
+
+def weights_for(fx):
+    cfg = O.config_named(fx["config"])
+    sd = O.random_state_dict(cfg, fx["weight_seed"])
+    tot = sum(float(v.double().sum()) for v in sd.values())
+    sq = sum(float((v.double() ** 2).sum()) for v in sd.values())
+    assert abs(tot - float(fx["weight_checksum"][0])) < 1e-6 * max(1.0, abs(tot))
+    assert abs(sq - float(fx["weight_checksum"][1])) < 1e-9 * sq
+    return cfg, sd
+
+
+def test_edge_index_kat():
+    fx = load_golden("kat_edge_index")
+    ei = O.fully_connected_edge_index(fx["batch_index"], fx["mask"])
+    assert ei.dtype == torch.int64 and torch.equal(ei, fx["edge_index"])
+    assert ei[0].tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 2] + [5] * 4 + [6] * 4 + [7] * 4 + [8] * 4
+    assert torch.equal(O.fully_connected_edge_index(fx["batch_index"], None), fx["edge_index_nomask"])
+
+
+def test_edge_index_empty_and_single():
+    bi = torch.zeros(3, dtype=torch.int64)
+    assert O.fully_connected_edge_index(bi, torch.zeros(3, dtype=torch.bool)).shape == (2, 0)
+    ei = O.fully_connected_edge_index(torch.zeros(1, dtype=torch.int64), None)
+    assert ei.tolist() == [[0], [0]]
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+def test_forward_matches_reference(name):
+    fx = load_golden(name)
+    cfg, sd = weights_for(fx)
+    taps = {}
+    out = O.denoiser_forward(sd, cfg, fx["batch_index"], fx["mask"], fx["xh"], fx["t"], fx["context"], taps=taps)
+    ref = fx["net_out"]
+    tol = 2e-5 * max(1.0, ref.abs().max().item())
+    assert (out - ref).abs().max().item() <= tol
+    assert taps["edge_index"].shape[1] == fx["num_edges"]
+    if "edge_index" in fx:
+        assert torch.equal(taps["edge_index"], fx["edge_index"])
+        assert (taps["f_ij"] - fx["f_ij"]).abs().max().item() <= 1e-6
+        assert (taps["e"] - fx["e"]).abs().max().item() <= 1e-5
+        assert (taps["xi"] - fx["xi"]).abs().max().item() <= 1e-5
+        for mine, theirs in zip(taps["layers"], fx["layers"]):
+            for k in ("h", "chi", "x"):
+                scale = max(1.0, theirs[k].abs().max().item())
+                assert (mine[k] - theirs[k]).abs().max().item() <= 2e-5 * scale, k
+
+
+@pytest.mark.parametrize("name", ["chain_qm9_T6", "chain_qm9_cond_T4", "chain_geom_T3"])
+def test_chain_matches_reference(name):
+    fx = load_golden(name)
+    cfg, sd = weights_for(fx)
+    assert torch.equal(O.gamma_table(cfg.num_timesteps, cfg.noise_precision, cfg.schedule_power), fx["gamma"])
+    torch.manual_seed(fx["noise_seed"])
+    out, bi, mask, z0 = O.sample_chain(sd, cfg, torch.tensor(fx["sizes"]), lambda s: torch.randn(s),
+                                       num_timesteps=fx["steps"], context=fx["context"], return_z0=True)
+    rel = (z0 - fx["z_0"]).abs().max().item() / fx["z_0"].abs().max().item()
+    assert rel < 1e-3
+    a = cfg.num_atom_types
+    assert torch.equal(out[:, 3:3 + a], fx["out"][:, 3:3 + a])
+    relx = (out[:, :3] - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
+    assert relx < 1e-3
+
+
+def test_se3_equivariance_of_oracle():
+    """Rotation + translation of x rotates vel and leaves h invariant (reflection is NOT a symmetry)."""
+    cfg = O.config_named("qm9")
+    sd = O.random_state_dict(cfg, 3)
+    g = torch.Generator().manual_seed(5)
+    sizes = [6, 4]
+    bi = torch.repeat_interleave(torch.arange(2), torch.tensor(sizes))
+    mask = torch.ones(10, dtype=torch.bool)
+    xh = torch.randn((10, 9), generator=g)
+    _, xc = O.centralize(xh[:, :3], bi, mask, 2)
+    t = torch.full((10, 1), 0.3)
+    A = torch.randn((3, 3), generator=g)
+    Q, _ = torch.linalg.qr(A)
+    if torch.det(Q) < 0:
+        Q[:, 0] = -Q[:, 0]
+    o1 = O.denoiser_forward(sd, cfg, bi, mask, torch.cat((xc, xh[:, 3:]), -1), t, dtype=torch.float64)
+    o2 = O.denoiser_forward(sd, cfg, bi, mask, torch.cat((xc @ Q.T, xh[:, 3:]), -1), t, dtype=torch.float64)
+    assert (o2[:, :3] - o1[:, :3] @ Q.double().T).abs().max() < 1e-6
+    assert (o2[:, 3:] - o1[:, 3:]).abs().max() < 1e-6
