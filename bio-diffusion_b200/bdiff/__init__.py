@@ -1,0 +1,13 @@
+"""bdiff — B200-native GCPNet denoiser hot path of GCDM (bio-diffusion).
+
+Public surface (mirrors the reference's seam):
+    GCPNetDynamicsB200   drop-in for src.models.components.gcpnet.GCPNetDynamics
+    GCDMSampler          inner loop of EquivariantVariationalDiffusion.mol_gen_sample
+    DenoiserConfig       dims derived from the reference's Hydra config groups
+"""
+from .config import DenoiserConfig, parameter_shapes
+from .dynamics import GCPNetDynamicsB200
+from .sampler import GCDMSampler
+from ._lib import BdiffError, load as load_library
+
+__all__ = ["DenoiserConfig", "parameter_shapes", "GCPNetDynamicsB200", "GCDMSampler", "BdiffError", "load_library"]

@@ -1,0 +1,201 @@
+"""GCPNetDynamicsB200 — drop-in for the reference's `GCPNetDynamics` (src/models/components/gcpnet.py:933-1232).
+
+Same constructor signature, same parameter names/shapes (so `load_state_dict` of reference checkpoints works
+with strict=True, state-dict prefix `ddpm.dynamics_network.`), same call contract
+
+    forward(batch, xh[N,3+F], t[N,1], **kwargs) -> (batch, net_out[N,3+F])
+
+but every arithmetic step runs in libbdiff_sm100.so (hand-written sm_100a kernels).  To plug it into the
+reference, add it to the `dynamics_networks` dict of src/models/qm9_mol_gen_ddpm.py:101-105.
+There is no CPU / PyTorch fallback: tensors must live on a CUDA device and the library must be built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import DenoiserConfig, parameter_shapes
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter names."""
+
+
+def _register(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if p not in mod._modules:
+            mod.add_module(p, _Node())
+        mod = mod._modules[p]
+    mod.register_parameter(parts[-1], param)
+
+
+class GCPNetDynamicsB200(nn.Module):
+    def __init__(self, model_cfg=None, module_cfg=None, layer_cfg=None, diffusion_cfg=None, dataloader_cfg=None,
+                 *, config: Optional[DenoiserConfig] = None, mode: str = "parity"):
+        super().__init__()
+        self.cfg = config if config is not None else DenoiserConfig.from_reference_cfgs(
+            model_cfg, module_cfg, layer_cfg, diffusion_cfg, dataloader_cfg)
+        self.num_x_dims = 3
+        self.num_context_node_features = self.cfg.num_context
+        self.mode = mode
+        self._shapes = parameter_shapes(self.cfg)
+        for name, shape in self._shapes.items():
+            _register(self, name, nn.Parameter(torch.empty(shape)))
+        self.reset_parameters()
+        self._handle = None          # bdiff_handle* (created lazily on the first CUDA call)
+        self._weights_key = None
+        self._plan_key = None
+        self._plan_info = None       # (B, N, E)
+        self._keepalive = None
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def reset_parameters(self) -> None:
+        """nn.Linear's default init (kaiming-uniform, bound 1/sqrt(fan_in)) for every weight/bias pair."""
+        with torch.no_grad():
+            for name, p in self.named_parameters():
+                if name.endswith("weight"):
+                    fan_in = p.shape[1]
+                else:
+                    fan_in = self._shapes[name[:-4] + "weight"][1]
+                bound = 1.0 / math.sqrt(fan_in)
+                p.uniform_(-bound, bound)
+
+    # ------------------------------------------------------------------------------------------ C-ABI handle
+    def _ensure_handle(self):
+        if self._handle is not None:
+            return self._handle
+        lib = _lib.load()
+        c = self.cfg
+        cfg = _lib.Config(num_h=c.num_h, num_context=c.num_context, num_layers=c.num_layers, h_hidden=c.h_hidden,
+                          chi_hidden=c.chi_hidden, e_hidden=c.e_hidden, xi_hidden=c.xi_hidden,
+                          mode=_lib.MODE_TENSOR if self.mode == "tensor" else _lib.MODE_PARITY_FP32)
+        h = C.c_void_p()
+        rc = lib.bdiff_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise _lib.BdiffError(f"bdiff_create failed (code {rc}): {lib.bdiff_last_error(None).decode()}")
+        self._handle = h
+        return h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().bdiff_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream() -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def sync_weights(self, force: bool = False) -> None:
+        """Repack the module's parameters into the kernel layout (bdiff_set_weight per tensor)."""
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if not force and key == self._weights_key:
+            return
+        lib = _lib.load()
+        h = self._ensure_handle()
+        st = self._stream()
+        for name, p in self.named_parameters():
+            if not p.is_cuda:
+                raise _lib.BdiffError("GCPNetDynamicsB200 parameters must be on a CUDA device (no CPU fallback)")
+            t = p.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(h, lib.bdiff_set_weight(h, st, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()),
+                       f"bdiff_set_weight({name})")
+        missing = lib.bdiff_weights_missing(h)
+        if missing != 0:
+            raise _lib.BdiffError(f"{missing} parameter tensors were not set")
+        self._weights_key = key
+
+    def plan(self, batch_index: torch.Tensor, mask: torch.Tensor, num_mols: Optional[int] = None) -> Tuple[int, int, int]:
+        """Build (or reuse) the implicit edge plan for (batch_index, mask): replaces get_fully_connected_edge_index."""
+        key = (batch_index.data_ptr(), batch_index._version, mask.data_ptr(), mask._version, batch_index.shape[0])
+        if key == self._plan_key:
+            return self._plan_info
+        if not batch_index.is_cuda:
+            raise _lib.BdiffError("batch_index must be a CUDA tensor (no CPU fallback)")
+        lib = _lib.load()
+        h = self._ensure_handle()
+        bi = batch_index.to(torch.int64).contiguous()
+        mk = mask.to(torch.uint8).contiguous()
+        n = bi.shape[0]
+        b = int(num_mols) if num_mols is not None else int(bi[-1].item()) + 1
+        e = C.c_int64(0)
+        _lib.check(h, lib.bdiff_plan_topology(h, self._stream(), b, n, C.c_void_p(bi.data_ptr()),
+                                              C.c_void_p(mk.data_ptr()), C.byref(e)), "bdiff_plan_topology")
+        self._plan_key = key
+        self._plan_info = (b, n, int(e.value))
+        self._keepalive = (batch_index, mask)
+        return self._plan_info
+
+    def edge_index(self) -> torch.Tensor:
+        """The reference's edge_index int64 [2, E] for the current plan (bit-exact; built on demand)."""
+        lib = _lib.load()
+        _, _, e = self._plan_info
+        dev = self._keepalive[0].device
+        out = torch.empty((2, e), dtype=torch.int64, device=dev)
+        _lib.check(self._handle, lib.bdiff_edge_index(self._handle, self._stream(), C.c_void_p(out.data_ptr())),
+                   "bdiff_edge_index")
+        return out
+
+    def debug_tap(self, which: str) -> torch.Tensor:
+        """Copy of an intermediate tensor of the last forward (parity tests)."""
+        lib = _lib.load()
+        rows, cols = C.c_int64(), C.c_int64()
+        _lib.check(self._handle, lib.bdiff_debug_tap(self._handle, self._stream(), which.encode(), None,
+                                                     C.byref(rows), C.byref(cols)), f"bdiff_debug_tap({which})")
+        out = torch.empty((rows.value, cols.value), dtype=torch.float32, device=self._keepalive[0].device)
+        _lib.check(self._handle, lib.bdiff_debug_tap(self._handle, self._stream(), which.encode(),
+                                                     C.c_void_p(out.data_ptr()), C.byref(rows), C.byref(cols)),
+                   f"bdiff_debug_tap({which})")
+        return out
+
+    # ------------------------------------------------------------------------------------------ forward
+    def denoise(self, batch_index: torch.Tensor, mask: torch.Tensor, xh: torch.Tensor, t: torch.Tensor,
+                context: Optional[torch.Tensor] = None, num_mols: Optional[int] = None) -> torch.Tensor:
+        if not xh.is_cuda:
+            raise _lib.BdiffError("GCPNetDynamicsB200 runs on CUDA tensors only (no CPU fallback)")
+        lib = _lib.load()
+        self.sync_weights()
+        _, n, _ = self.plan(batch_index, mask, num_mols)
+        xh_c = xh.detach().to(torch.float32).contiguous()
+        t_c = t.detach().to(torch.float32).reshape(-1).contiguous()
+        if t_c.numel() == 1:
+            t_c = t_c.expand(n).contiguous()
+        if xh_c.shape != (n, 3 + self.cfg.num_h) or t_c.shape[0] != n:
+            raise ValueError(f"xh must be [{n},{3 + self.cfg.num_h}] and t [{n},1]")
+        ctx_ptr = None
+        if self.cfg.num_context:
+            if context is None:
+                raise ValueError("this configuration is property-conditional: batch.props_context is required")
+            ctx_c = context.detach().to(torch.float32).reshape(n, self.cfg.num_context).contiguous()
+            ctx_ptr = C.c_void_p(ctx_c.data_ptr())
+        out = torch.empty_like(xh_c)
+        _lib.check(self._handle, lib.bdiff_denoise_forward(
+            self._handle, self._stream(), C.c_void_p(xh_c.data_ptr()), C.c_void_p(t_c.data_ptr()), ctx_ptr,
+            C.c_void_p(out.data_ptr())), "bdiff_denoise_forward")
+        return out
+
+    def forward(self, batch: Any, xh: torch.Tensor, t: torch.Tensor, **kwargs: Any):
+        """Reference contract: gcpnet.py:1042-1052.  Reads batch.batch / batch.mask / batch.props_context."""
+        if kwargs.get("xh_self_cond") is not None or kwargs.get("x_self_cond") is not None:
+            raise NotImplementedError("self-conditioning is not supported (shipped configs have self_condition=false)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and xh.requires_grad:
+            raise NotImplementedError("backward through GCPNetDynamicsB200 is not implemented yet (inference path)")
+        ctx = getattr(batch, "props_context", None)
+        num_mols = getattr(batch, "num_graphs", None)
+        net_out = self.denoise(batch.batch, batch.mask, xh, t, ctx, num_mols if isinstance(num_mols, int) else None)
+        return batch, net_out
+
+    def launch_count(self) -> int:
+        return int(_lib.load().bdiff_launch_count(self._handle)) if self._handle is not None else 0

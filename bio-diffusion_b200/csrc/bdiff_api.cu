@@ -1,0 +1,531 @@
+// bdiff_api.cu — the C ABI declared in include/bdiff.h: handle, weight repacking, topology plan, forward,
+// reverse step.  Host-side logic only; kernels live in bdiff_kernels_fp32.cu / bdiff_edge_tc.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/bdiff.h"
+#include "bdiff_kernels.h"
+
+using namespace bdiff;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return e;
+    bytes = need;
+    return cudaMemset(p, 0, need);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct bdiff_handle {
+  bdiff_config cfg{};
+  Dims d{};
+  std::string err;
+  int64_t launches = 0;
+
+  // packed weights
+  float* wbuf = nullptr;
+  size_t wfloats = 0, wused = 0;
+  std::vector<LayerW> layers;
+  EmbedW embed{};
+  std::map<std::string, bool> seen;   // reference parameter name -> set?
+
+  // plan
+  bool have_plan = false;
+  Plan plan{};
+  DevBuf plan_buf;
+  int Npad = 0;
+  long long Epad = 0;
+
+  // workspace
+  DevBuf work_buf;
+  Work work{};
+  DevBuf eps_buf;      // [N,3+F] denoiser output inside reverse_step / decode
+  DevBuf tu_buf;       // uniform t scalar
+
+  // tensor-core path state (bdiff_edge_tc.cu)
+  void* tc_state = nullptr;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  float* walloc(size_t n) {
+    n = (n + 63) / 64 * 64;   // 256-byte granularity keeps every matrix 16 B aligned for bulk copies
+    float* r = wbuf + wused;
+    wused += n;
+    return r;
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ weight layout
+void gcp_names(std::map<std::string, bool>& seen, const std::string& p, bool ff, bool vout) {
+  seen[p + "vector_down.weight"] = false;
+  seen[p + "vector_down_frames.weight"] = false;
+  if (ff) {
+    seen[p + "scalar_out.0.weight"] = false; seen[p + "scalar_out.0.bias"] = false;
+    seen[p + "scalar_out.2.weight"] = false; seen[p + "scalar_out.2.bias"] = false;
+  } else {
+    seen[p + "scalar_out.weight"] = false; seen[p + "scalar_out.bias"] = false;
+  }
+  if (vout) {
+    seen[p + "vector_up.weight"] = false;
+    seen[p + "vector_out_scale.weight"] = false; seen[p + "vector_out_scale.bias"] = false;
+  }
+}
+
+size_t layout_weights(bdiff_handle* h, bool assign) {
+  // When !assign only the size is computed (wbuf is null); offsets are deterministic so a second pass assigns.
+  const Dims& d = h->d;
+  h->wused = 0;
+  auto A = [&](size_t n) -> float* { float* r = h->walloc(n); return assign ? r : nullptr; };
+  EmbedW& e = h->embed;
+  e.eWs = A((size_t)d.Ke * d.Ed); e.ebs = A(d.Ed); e.ewd = A(d.Xd); e.ewf = A(4);
+  e.eWu = A((size_t)d.Xd * d.Xd); e.eWg = A((size_t)d.Ed * d.Xd); e.ebg = A(d.Xd);
+  e.nWs = A((size_t)d.Kn * 256); e.nbs = A(256); e.nWd = A(2 * 32); e.nWf = A(2 * 3 + 2);
+  e.nWu = A(32 * 32); e.nWg = A(256 * 32); e.nbg = A(32);
+  e.pWs = A((size_t)300 * d.Hin); e.pbs = A(d.Hin); e.pWd = A(32 * 32); e.pWf = A(32 * 3);
+  h->layers.assign(d.L, LayerW{});
+  for (int l = 0; l < d.L; ++l) {
+    LayerW& w = h->layers[l];
+    w.W0e = A((size_t)d.K0 * 256); w.Wsi = A(256 * 256); w.Wsj = A(256 * 256); w.b0 = A(256);
+    w.Wd0i = A(32 * d.hid0); w.Wd0x = A((size_t)d.Xd * d.hid0); w.Wd0j = A(32 * d.hid0);
+    w.Wf0i = A(32 * 3); w.Wf0x = A(d.Xd * 3); w.Wf0j = A(32 * 3);
+    w.Wu0 = A(d.hid0 * 32); w.Wg0 = A(256 * 32); w.bg0 = A(32);
+    for (int k = 0; k < 3; ++k) {
+      w.Wk[k] = A((size_t)kKM * 256); w.bk[k] = A(256); w.Wdk[k] = A(32 * kHidM); w.Wfk[k] = A(32 * 3);
+      w.Wuk[k] = A(kHidM * 32); w.Wgk[k] = A(256 * 32); w.bgk[k] = A(32);
+    }
+    w.wa = A(256); w.ba = A(4);
+    w.W1 = A((size_t)kKFF * 256); w.b1 = A(256); w.W2 = A(256 * 256); w.b2 = A(256);
+    w.Wdf = A(64 * kHidFF); w.Wff = A(64 * 3); w.Wuf = A(kHidFF * 32); w.Wgf = A(256 * 32); w.bgf = A(32);
+    w.Wp = A((size_t)kKM * 256); w.bp = A(256); w.Wdp = A(32 * kHidM); w.Wfp = A(32 * 3);
+    w.Wup = A(kHidM); w.Wgp = A(256); w.bgp = A(4);
+  }
+  return h->wused;
+}
+
+struct PackOp {
+  const float* dst; int dst_ld; int col0; int ncols; int kpad; int nout;
+};
+
+// Resolve a reference parameter name to its pack operations + expected shape.
+bool resolve(bdiff_handle* h, const std::string& name, std::vector<PackOp>& ops, int64_t& rows, int64_t& cols) {
+  const Dims& d = h->d;
+  auto W = [&](const float* dst, int dst_ld, int col0, int ncols, int kpad, int nout) {
+    ops.push_back(PackOp{dst, dst_ld, col0, ncols, kpad, nout});
+  };
+  auto gcp = [&](const std::string& leaf, const float* Ws, int s_in, int kpad_s, int nout_s, const float* bs,
+                 const float* Wd, int v_in, int hid, const float* Wf, const float* Wu, int v_out,
+                 const float* Wg, const float* bg) -> bool {
+    const int fan = s_in + hid + 9;
+    if (leaf == "scalar_out.weight") { rows = nout_s; cols = fan; W(Ws, nout_s, 0, fan, kpad_s, nout_s); return true; }
+    if (leaf == "scalar_out.bias") { rows = nout_s; cols = 1; W(bs, nout_s, 0, 1, 1, nout_s); return true; }
+    if (leaf == "vector_down.weight") { rows = hid; cols = v_in; W(Wd, hid, 0, v_in, v_in, hid); return true; }
+    if (leaf == "vector_down_frames.weight") { rows = 3; cols = v_in; W(Wf, 3, 0, v_in, v_in, 3); return true; }
+    if (Wu && leaf == "vector_up.weight") { rows = v_out; cols = hid; W(Wu, v_out, 0, hid, hid, v_out); return true; }
+    if (Wg && leaf == "vector_out_scale.weight") { rows = v_out; cols = nout_s; W(Wg, v_out, 0, nout_s, nout_s, v_out); return true; }
+    if (bg && leaf == "vector_out_scale.bias") { rows = v_out; cols = 1; W(bg, v_out, 0, 1, 1, v_out); return true; }
+    return false;
+  };
+  const EmbedW& e = h->embed;
+  const std::string pe = "gcp_embedding.edge_embedding.", pn = "gcp_embedding.node_embedding.",
+                    pp = "scalar_node_projection_gcp.";
+  if (name.rfind(pe, 0) == 0)
+    return gcp(name.substr(pe.size()), e.eWs, 1, d.Ke, d.Ed, e.ebs, e.ewd, 1, d.Xd, e.ewf, e.eWu, d.Xd, e.eWg, e.ebg);
+  if (name.rfind(pn, 0) == 0)
+    return gcp(name.substr(pn.size()), e.nWs, d.Hin, d.Kn, 256, e.nbs, e.nWd, 2, 32, e.nWf, e.nWu, 32, e.nWg, e.nbg);
+  if (name.rfind(pp, 0) == 0)
+    return gcp(name.substr(pp.size()), e.pWs, 256, 300, d.Hin, e.pbs, e.pWd, 32, 32, e.pWf, nullptr, 0, nullptr, nullptr);
+  int l = -1, consumed = 0;
+  if (sscanf(name.c_str(), "interaction_layers.%d.%n", &l, &consumed) != 1 || l < 0 || l >= d.L) return false;
+  const std::string rest = name.substr(consumed);
+  const LayerW& w = h->layers[l];
+  const std::string pm = "interaction.message_fusion.", pa = "interaction.scalar_message_attention.0.",
+                    pf = "feedforward_network.0.", px = "node_position_update_gcp.";
+  if (rest.rfind(pm, 0) == 0) {
+    int k = -1, c2 = 0;
+    if (sscanf(rest.c_str() + pm.size(), "%d.%n", &k, &c2) != 1 || k < 0 || k > 3) return false;
+    const std::string leaf = rest.substr(pm.size() + c2);
+    if (k > 0)
+      return gcp(leaf, w.Wk[k - 1], 256, kKM, 256, w.bk[k - 1], w.Wdk[k - 1], 32, kHidM, w.Wfk[k - 1], w.Wuk[k - 1],
+                 32, w.Wgk[k - 1], w.bgk[k - 1]);
+    // k == 0: split form.  Torch columns of scalar_out: [h_row(256) | e(Ed) | h_col(256) | vn(hid0) | q(9)],
+    // of vector_down / vector_down_frames: [chi_row(32) | xi(Xd) | chi_col(32)]   (gcpnet.py:694)
+    const int fan = 512 + d.Ed + d.hid0 + 9, vin = 64 + d.Xd;
+    if (leaf == "scalar_out.weight") {
+      rows = 256; cols = fan;
+      W(w.Wsi, 256, 0, 256, 256, 256);
+      W(w.Wsj, 256, 256 + d.Ed, 256, 256, 256);
+      W(w.W0e, 256, 256, d.Ed, d.Ed, 256);                                             // e rows
+      W(w.W0e + (size_t)d.Ed * 256, 256, 512 + d.Ed, d.hid0 + 9, d.K0 - d.Ed, 256);     // vn, q rows + zero pad
+      return true;
+    }
+    if (leaf == "scalar_out.bias") { rows = 256; cols = 1; W(w.b0, 256, 0, 1, 1, 256); return true; }
+    if (leaf == "vector_down.weight") {
+      rows = d.hid0; cols = vin;
+      W(w.Wd0i, d.hid0, 0, 32, 32, d.hid0); W(w.Wd0x, d.hid0, 32, d.Xd, d.Xd, d.hid0);
+      W(w.Wd0j, d.hid0, 32 + d.Xd, 32, 32, d.hid0);
+      return true;
+    }
+    if (leaf == "vector_down_frames.weight") {
+      rows = 3; cols = vin;
+      W(w.Wf0i, 3, 0, 32, 32, 3); W(w.Wf0x, 3, 32, d.Xd, d.Xd, 3); W(w.Wf0j, 3, 32 + d.Xd, 32, 32, 3);
+      return true;
+    }
+    if (leaf == "vector_up.weight") { rows = 32; cols = d.hid0; W(w.Wu0, 32, 0, d.hid0, d.hid0, 32); return true; }
+    if (leaf == "vector_out_scale.weight") { rows = 32; cols = 256; W(w.Wg0, 32, 0, 256, 256, 32); return true; }
+    if (leaf == "vector_out_scale.bias") { rows = 32; cols = 1; W(w.bg0, 32, 0, 1, 1, 32); return true; }
+    return false;
+  }
+  if (rest.rfind(pa, 0) == 0) {
+    const std::string leaf = rest.substr(pa.size());
+    if (leaf == "weight") { rows = 1; cols = 256; W(w.wa, 1, 0, 256, 256, 1); return true; }
+    if (leaf == "bias") { rows = 1; cols = 1; W(w.ba, 1, 0, 1, 1, 1); return true; }
+    return false;
+  }
+  if (rest.rfind(pf, 0) == 0) {
+    const std::string leaf = rest.substr(pf.size());
+    if (leaf == "scalar_out.0.weight") { rows = 256; cols = 537; W(w.W1, 256, 0, 537, kKFF, 256); return true; }
+    if (leaf == "scalar_out.0.bias") { rows = 256; cols = 1; W(w.b1, 256, 0, 1, 1, 256); return true; }
+    if (leaf == "scalar_out.2.weight") { rows = 256; cols = 256; W(w.W2, 256, 0, 256, 256, 256); return true; }
+    if (leaf == "scalar_out.2.bias") { rows = 256; cols = 1; W(w.b2, 256, 0, 1, 1, 256); return true; }
+    return gcp(leaf, nullptr, 512, 0, 256, nullptr, w.Wdf, 64, kHidFF, w.Wff, w.Wuf, 32, w.Wgf, w.bgf);
+  }
+  if (rest.rfind(px, 0) == 0)
+    return gcp(rest.substr(px.size()), w.Wp, 256, kKM, 256, w.bp, w.Wdp, 32, kHidM, w.Wfp, w.Wup, 1, w.Wgp, w.bgp);
+  return false;
+}
+
+cudaError_t ensure_work(bdiff_handle* h) {
+  const Dims& d = h->d;
+  const size_t Np = h->Npad, Ep = (size_t)h->Epad;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
+  const size_t o_xi = take(Np * 3), o_x = take(Np * 3), o_hin = take(Np * d.Hin), o_chin = take(Np * 6),
+               o_fbar = take(Np * 12), o_h = take(Np * 256), o_chi = take(Np * 96), o_PI = take(Np * kPStride),
+               o_PJ = take(Np * kPStride), o_agg = take(Np * kMsg), o_hp = take(Np * 32),
+               o_e = take(Ep * d.Ed), o_xie = take(Ep * d.Xd * 3), o_fr = take(Ep * 9), o_flag = take(64);
+  cudaError_t e = h->work_buf.ensure(off * sizeof(float));
+  if (e != cudaSuccess) return e;
+  float* b = static_cast<float*>(h->work_buf.p);
+  Work& w = h->work;
+  w.x_init = b + o_xi; w.x = b + o_x; w.h_in = b + o_hin; w.chi_in = b + o_chin; w.fbar = b + o_fbar;
+  w.h = b + o_h; w.chi = b + o_chi; w.PI = b + o_PI; w.PJ = b + o_PJ; w.agg = b + o_agg; w.hproj = b + o_hp;
+  w.e = b + o_e; w.xi = b + o_xie; w.frames = b + o_fr; w.nan_flag = reinterpret_cast<int*>(b + o_flag);
+  e = h->eps_buf.ensure(Np * (3 + d.F) * sizeof(float));
+  if (e != cudaSuccess) return e;
+  return h->tu_buf.ensure(256);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t bdiff_abi_version(void) { return BDIFF_ABI_VERSION; }
+
+const char* bdiff_last_error(const bdiff_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return BDIFF_EINVAL; }
+  *out = nullptr;
+  if (cfg->h_hidden != 256 || cfg->chi_hidden != 32) { g_create_error = "h_hidden must be 256 and chi_hidden 32"; return BDIFF_EINVAL; }
+  if (cfg->e_hidden < 4 || cfg->e_hidden > 64 || cfg->e_hidden % 4) { g_create_error = "e_hidden must be a multiple of 4 in [4,64]"; return BDIFF_EINVAL; }
+  if (cfg->xi_hidden < 4 || cfg->xi_hidden > 16 || cfg->xi_hidden % 4) { g_create_error = "xi_hidden must be a multiple of 4 in [4,16]"; return BDIFF_EINVAL; }
+  if (cfg->num_h < 1 || cfg->num_context < 0 || cfg->num_h + 1 + cfg->num_context > 28) { g_create_error = "num_h + 1 + num_context must be in [2,28]"; return BDIFF_EINVAL; }
+  if (cfg->num_layers < 1 || cfg->num_layers > 64) { g_create_error = "num_layers out of range"; return BDIFF_EINVAL; }
+  if (cfg->mode != BDIFF_MODE_PARITY_FP32 && cfg->mode != BDIFF_MODE_TENSOR) { g_create_error = "unknown mode"; return BDIFF_EINVAL; }
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+    g_create_error = "no CUDA device: libbdiff_sm100 has no CPU fallback";
+    return BDIFF_ECUDA;
+  }
+  cudaDeviceProp prop{};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) {
+    g_create_error = "libbdiff_sm100 is built for sm_100a (B200) only; found compute capability " +
+                     std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return BDIFF_ECUDA;
+  }
+  bdiff_handle* h = new bdiff_handle();
+  h->cfg = *cfg;
+  Dims& d = h->d;
+  d.F = cfg->num_h; d.C = cfg->num_context; d.Hin = d.F + 1 + d.C; d.Ed = cfg->e_hidden; d.Xd = cfg->xi_hidden;
+  d.hid0 = (64 + d.Xd) / 4;
+  d.K0 = round_up(d.Ed + d.hid0 + 9, 4);
+  d.Ke = round_up(1 + d.Xd + 9, 4);
+  d.Kn = round_up(d.Hin + 32 + 9, 4);
+  d.L = cfg->num_layers;
+  if ((64 + d.Xd) % 4) { g_create_error = "2*chi_hidden + xi_hidden must be divisible by the bottleneck 4"; delete h; return BDIFF_EINVAL; }
+  const size_t need = layout_weights(h, false);
+  if (cudaMalloc(&h->wbuf, need * sizeof(float)) != cudaSuccess) { g_create_error = "cudaMalloc(weights) failed"; delete h; return BDIFF_ENOMEM; }
+  cudaMemset(h->wbuf, 0, need * sizeof(float));
+  h->wfloats = need;
+  layout_weights(h, true);
+  // the set of reference parameter names this configuration must receive
+  gcp_names(h->seen, "gcp_embedding.edge_embedding.", false, true);
+  gcp_names(h->seen, "gcp_embedding.node_embedding.", false, true);
+  gcp_names(h->seen, "scalar_node_projection_gcp.", false, false);
+  for (int l = 0; l < d.L; ++l) {
+    const std::string p = "interaction_layers." + std::to_string(l) + ".";
+    for (int k = 0; k < 4; ++k) gcp_names(h->seen, p + "interaction.message_fusion." + std::to_string(k) + ".", false, true);
+    h->seen[p + "interaction.scalar_message_attention.0.weight"] = false;
+    h->seen[p + "interaction.scalar_message_attention.0.bias"] = false;
+    gcp_names(h->seen, p + "feedforward_network.0.", true, true);
+    gcp_names(h->seen, p + "node_position_update_gcp.", false, true);
+  }
+  cudaError_t e = configure_kernels();
+  if (e != cudaSuccess) {
+    g_create_error = std::string("configure_kernels: ") + cudaGetErrorString(e);
+    cudaFree(h->wbuf);
+    delete h;
+    return BDIFF_ECUDA;
+  }
+  *out = h;
+  return BDIFF_OK;
+}
+
+void bdiff_destroy(bdiff_handle* h) {
+  if (!h) return;
+  if (h->wbuf) cudaFree(h->wbuf);
+  h->plan_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release();
+  delete h;
+}
+
+int32_t bdiff_set_weight(bdiff_handle* h, void* stream, const char* name, const float* data, const int64_t* shape,
+                         int32_t ndim) {
+  if (!h || !name || !data || !shape || ndim < 1 || ndim > 2) return h ? h->fail(BDIFF_EINVAL, "bad argument") : BDIFF_EINVAL;
+  auto it = h->seen.find(name);
+  if (it == h->seen.end()) return h->fail(BDIFF_EINVAL, "unknown parameter name '%s'", name);
+  std::vector<PackOp> ops;
+  int64_t rows = 0, cols = 0;
+  if (!resolve(h, name, ops, rows, cols)) return h->fail(BDIFF_EINVAL, "cannot place parameter '%s'", name);
+  const int64_t got_rows = shape[0], got_cols = ndim == 2 ? shape[1] : 1;
+  if (got_rows != rows || got_cols != cols)
+    return h->fail(BDIFF_EINVAL, "parameter '%s': expected shape [%lld,%lld], got [%lld,%lld]", name, (long long)rows,
+                   (long long)cols, (long long)got_rows, (long long)got_cols);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (const PackOp& op : ops) {
+    launch_pack(st, const_cast<float*>(op.dst), op.dst_ld, data, (int)cols, op.col0, op.ncols, op.kpad, op.nout);
+    h->launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "pack '%s': %s", name, cudaGetErrorString(e));
+  it->second = true;
+  return BDIFF_OK;
+}
+
+int32_t bdiff_weights_missing(const bdiff_handle* h) {
+  if (!h) return BDIFF_EINVAL;
+  int n = 0;
+  for (auto& kv : h->seen) n += kv.second ? 0 : 1;
+  return n;
+}
+
+int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int64_t num_nodes,
+                            const int64_t* batch_index, const uint8_t* mask, int64_t* num_edges_host) {
+  if (!h) return BDIFF_EINVAL;
+  if (num_mols < 1 || num_nodes < 1 || !batch_index || !mask) return h->fail(BDIFF_EINVAL, "bad plan arguments");
+  if (num_nodes > (1ll << 30)) return h->fail(BDIFF_EINVAL, "too many nodes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = (int)num_nodes, B = num_mols;
+  std::vector<int64_t> bi(N);
+  std::vector<uint8_t> mk(N);
+  cudaError_t e = cudaMemcpyAsync(bi.data(), batch_index, N * sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(mk.data(), mask, N, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "plan D2H: %s", cudaGetErrorString(e));
+  std::vector<int> mol_off(B + 1, 0), act_off(B + 1, 0), act_idx, node_mol(N);
+  std::vector<long long> edge_off(B + 1, 0);
+  act_idx.reserve(N);
+  int64_t prev = 0;
+  for (int i = 0; i < N; ++i) {
+    const int64_t m = bi[i];
+    if (m < 0 || m >= B) return h->fail(BDIFF_EINVAL, "batch_index[%d]=%lld outside [0,%d)", i, (long long)m, B);
+    if (m < prev) return h->fail(BDIFF_EINVAL, "batch_index must be sorted (node %d)", i);
+    prev = m;
+    mol_off[m + 1]++;
+    node_mol[i] = (int)m;
+  }
+  for (int k = 0; k < B; ++k) mol_off[k + 1] += mol_off[k];
+  for (int k = 0; k < B; ++k) {
+    for (int i = mol_off[k]; i < mol_off[k + 1]; ++i)
+      if (mk[i]) act_idx.push_back(i);
+    act_off[k + 1] = (int)act_idx.size();
+    const long long na = act_off[k + 1] - act_off[k];
+    edge_off[k + 1] = edge_off[k] + na * na;
+  }
+  const long long E = edge_off[B];
+  if (E >= (1ll << 36)) return h->fail(BDIFF_EINVAL, "too many edges");
+  const size_t M = act_idx.size();
+  // device layout: [mol_off | act_off | act_idx | node_mol | edge_off(int64) | mask]
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_mo = take((B + 1) * 4), o_ao = take((B + 1) * 4), o_ai = take((M + 1) * 4), o_nm = take(N * 4),
+               o_eo = take((B + 1) * 8), o_mk = take(N);
+  std::vector<unsigned char> stage(off, 0);
+  memcpy(stage.data() + o_mo, mol_off.data(), (B + 1) * 4);
+  memcpy(stage.data() + o_ao, act_off.data(), (B + 1) * 4);
+  if (M) memcpy(stage.data() + o_ai, act_idx.data(), M * 4);
+  memcpy(stage.data() + o_nm, node_mol.data(), N * 4);
+  memcpy(stage.data() + o_eo, edge_off.data(), (B + 1) * 8);
+  memcpy(stage.data() + o_mk, mk.data(), N);
+  e = h->plan_buf.ensure(off);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->plan_buf.p, stage.data(), off, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "plan H2D: %s", cudaGetErrorString(e));
+  unsigned char* base = static_cast<unsigned char*>(h->plan_buf.p);
+  Plan& p = h->plan;
+  p.B = B; p.N = N; p.E = E;
+  p.mol_off = reinterpret_cast<int*>(base + o_mo);
+  p.act_off = reinterpret_cast<int*>(base + o_ao);
+  p.act_idx = reinterpret_cast<int*>(base + o_ai);
+  p.node_mol = reinterpret_cast<int*>(base + o_nm);
+  p.edge_off = reinterpret_cast<long long*>(base + o_eo);
+  p.mask = base + o_mk;
+  h->Npad = round_up(N, 16);
+  h->Epad = (E + 127) / 128 * 128 + 128;
+  e = ensure_work(h);
+  if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "workspace: %s", cudaGetErrorString(e));
+  h->have_plan = true;
+  if (num_edges_host) *num_edges_host = E;
+  return BDIFF_OK;
+}
+
+int32_t bdiff_edge_index(bdiff_handle* h, void* stream, int64_t* edge_index) {
+  if (!h || !edge_index) return BDIFF_EINVAL;
+  if (!h->have_plan) return h->fail(BDIFF_ESTATE, "no topology plan");
+  launch_edge_index(static_cast<cudaStream_t>(stream), h->plan, reinterpret_cast<long long*>(edge_index));
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "edge_index: %s", cudaGetErrorString(e));
+}
+
+static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, const float* t_nodes,
+                            const float* coef_table, const int* step_ptr, const float* context, float* net_out) {
+  if (!h->have_plan) return h->fail(BDIFF_ESTATE, "bdiff_plan_topology has not been called");
+  if (bdiff_weights_missing(h) != 0) {
+    for (auto& kv : h->seen)
+      if (!kv.second) return h->fail(BDIFF_ESTATE, "%d parameters not set, first missing: %s", bdiff_weights_missing(h), kv.first.c_str());
+  }
+  if (h->d.C > 0 && !context) return h->fail(BDIFF_EINVAL, "context required (num_context=%d)", h->d.C);
+  const Plan& p = h->plan;
+  const Dims& d = h->d;
+  const Work& w = h->work;
+  launch_prep(st, p, d, xh, t_nodes, coef_table, step_ptr, context, w);
+  launch_edge_embed(st, p, d, h->embed, w);
+  launch_node_embed(st, p, d, h->embed, h->layers[0], w);
+  h->launches += 4;
+  for (int l = 0; l < d.L; ++l) {
+    launch_edge_message(st, p, d, h->layers[l], w);
+    const bool last = (l == d.L - 1);
+    launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);
+    h->launches += 2;
+  }
+  launch_finalize(st, p, d, w, net_out);
+  h->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "forward: %s", cudaGetErrorString(e));
+}
+
+int32_t bdiff_denoise_forward(bdiff_handle* h, void* stream, const float* xh, const float* t, const float* context,
+                              float* net_out) {
+  if (!h || !xh || !t || !net_out) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
+  return forward_impl(h, static_cast<cudaStream_t>(stream), xh, t, nullptr, nullptr, context, net_out);
+}
+
+int32_t bdiff_debug_tap(bdiff_handle* h, void* stream, const char* which, float* dst, int64_t* rows, int64_t* cols) {
+  if (!h || !which || !rows || !cols) return BDIFF_EINVAL;
+  if (!h->have_plan) return h->fail(BDIFF_ESTATE, "no topology plan");
+  const std::string s = which;
+  const Work& w = h->work;
+  const Dims& d = h->d;
+  const int64_t N = h->plan.N, E = h->plan.E;
+  const float* src = nullptr;
+  if (s == "f_ij") { src = w.frames; *rows = E; *cols = 9; }
+  else if (s == "e") { src = w.e; *rows = E; *cols = d.Ed; }
+  else if (s == "xi") { src = w.xi; *rows = E; *cols = d.Xd * 3; }
+  else if (s == "h") { src = w.h; *rows = N; *cols = 256; }
+  else if (s == "chi") { src = w.chi; *rows = N; *cols = 96; }
+  else if (s == "x") { src = w.x; *rows = N; *cols = 3; }
+  else if (s == "fbar") { src = w.fbar; *rows = N; *cols = 12; }
+  else if (s == "chi_in") { src = w.chi_in; *rows = N; *cols = 6; }
+  else return h->fail(BDIFF_EINVAL, "unknown tap '%s'", which);
+  if (dst && *rows * *cols > 0) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)(*rows) * (*cols) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "tap copy: %s", cudaGetErrorString(e));
+  }
+  return BDIFF_OK;
+}
+
+int32_t bdiff_reverse_step(bdiff_handle* h, void* stream, float* z, const float* context, const float* noise_x,
+                           const float* noise_h, const float* coef_table, const int32_t* step_index) {
+  if (!h || !z || !noise_x || !noise_h || !coef_table) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* eps = static_cast<float*>(h->eps_buf.p);
+  int32_t rc = forward_impl(h, st, z, nullptr, coef_table, step_index, context, eps);
+  if (rc != BDIFF_OK) return rc;
+  launch_step(st, h->plan, h->d, 0, z, eps, noise_x, noise_h, coef_table, step_index, z);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "reverse_step: %s", cudaGetErrorString(e));
+}
+
+int32_t bdiff_decode_z0(bdiff_handle* h, void* stream, const float* z0, const float* context, const float* noise_x,
+                        const float* noise_h, const float* coef, float* xh) {
+  if (!h || !z0 || !noise_x || !noise_h || !coef || !xh) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* eps = static_cast<float*>(h->eps_buf.p);
+  int32_t rc = forward_impl(h, st, z0, nullptr, coef, nullptr, context, eps);
+  if (rc != BDIFF_OK) return rc;
+  launch_step(st, h->plan, h->d, 1, z0, eps, noise_x, noise_h, coef, nullptr, xh);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "decode_z0: %s", cudaGetErrorString(e));
+}
+
+int32_t bdiff_center_noise(bdiff_handle* h, void* stream, const float* noise_x, const float* noise_h, float* z) {
+  if (!h || !noise_x || !noise_h || !z) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
+  if (!h->have_plan) return h->fail(BDIFF_ESTATE, "no topology plan");
+  launch_step(static_cast<cudaStream_t>(stream), h->plan, h->d, 2, nullptr, nullptr, noise_x, noise_h, nullptr, nullptr, z);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "center_noise: %s", cudaGetErrorString(e));
+}
+
+int64_t bdiff_launch_count(const bdiff_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

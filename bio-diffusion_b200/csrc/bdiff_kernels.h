@@ -1,0 +1,50 @@
+// bdiff_kernels.h — host-visible launchers of the CUDA kernels (internal; the public surface is include/bdiff.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "bdiff_common.cuh"
+
+namespace bdiff {
+
+// Per-forward workspace (device, fp32).  Node buffers are padded to a multiple of 16 rows, edge buffers to a
+// multiple of 128 rows, and zero-initialised, so tile kernels never bounds-check their stores.
+struct Work {
+  float* x_init;   // [N,3]  masked input positions (un-centred)
+  float* x;        // [N,3]  current (centred, then updated) positions
+  float* h_in;     // [N,Hin]
+  float* chi_in;   // [N,2,3]
+  float* fbar;     // [N,12] mean frame of each node's row (9 used)
+  float* h;        // [N,256]
+  float* chi;      // [N,96]
+  float* PI;       // [N,328] endpoint projections for the next edge pass (row side, bias folded in)
+  float* PJ;       // [N,328] (col side)
+  float* agg;      // [N,352] aggregated messages
+  float* hproj;    // [N,32]  projected scalar outputs (Hin used)
+  float* e;        // [E,Ed]
+  float* xi;       // [E,Xd*3]
+  float* frames;   // [E,9]
+  int* nan_flag;
+};
+
+cudaError_t configure_kernels();
+size_t edge_smem_bytes();
+size_t node_smem_bytes();
+
+void launch_prep(cudaStream_t st, const Plan& p, const Dims& d, const float* xh, const float* t_nodes,
+                 const float* coef_table, const int* step_ptr, const float* ctx, const Work& w);
+void launch_edge_embed(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const Work& w);
+void launch_node_embed(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerW& l0,
+                       const Work& w);
+void launch_edge_message(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const Work& w);
+void launch_node_update(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
+                        const EmbedW& ew, const Work& w, int last);
+void launch_finalize(cudaStream_t st, const Plan& p, const Dims& d, const Work& w, float* out);
+void launch_step(cudaStream_t st, const Plan& p, const Dims& d, int mode, const float* z, const float* eps,
+                 const float* noise_x, const float* noise_h, const float* coef_table, const int* step_ptr,
+                 float* out);
+void launch_edge_index(cudaStream_t st, const Plan& p, long long* out);
+void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
+                 int kpad, int nout);
+
+}  // namespace bdiff

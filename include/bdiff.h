@@ -1,0 +1,134 @@
+/*
+ * bdiff.h — C ABI of libbdiff_sm100.so: the B200-native GCPNet denoiser hot path of GCDM.
+ *
+ * The reference (BioinfoMachineLearning/bio-diffusion) has no FFI for this path; its seam is the Python
+ * class contract `dynamics_network.forward(batch, xh, t) -> (batch, net_out)` selected in
+ * src/models/qm9_mol_gen_ddpm.py:101-105,125-131 (and geom_mol_gen_ddpm.py) and called from
+ * src/models/components/variational_diffusion.py:873,1042,1116,1236.  The entry points below are what a
+ * binding for that seam needs; each cites the reference interface it replaces.  Host mirror:
+ * bio-diffusion_b200/bdiff/dynamics.py (class GCPNetDynamicsB200); binding recipe: INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no torch types; every data pointer is a DEVICE pointer owned by the caller unless the name
+ *     ends in _host; float = fp32, indices int64 at the boundary (like the reference), mask = uint8 (0/1);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); nothing synchronises the
+ *     device except bdiff_plan_topology (one D2H of batch_index/mask + one H2D of the plan);
+ *   - return 0 on success, a negative BDIFF_E* code otherwise; never throws; bdiff_last_error(h) gives text;
+ *   - one handle per (device, stream); not thread-safe; the handle owns packed weights and workspace.
+ */
+#ifndef BDIFF_H_
+#define BDIFF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDIFF_OK 0
+#define BDIFF_EINVAL (-1)   /* bad argument / unsupported configuration            */
+#define BDIFF_ECUDA (-2)    /* a CUDA runtime call or kernel launch failed         */
+#define BDIFF_ESTATE (-3)   /* call order violated (weights missing, no plan, ...) */
+#define BDIFF_ENOMEM (-4)
+
+#define BDIFF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BDIFF_API __attribute__((visibility("default")))
+#else
+#define BDIFF_API
+#endif
+
+/* Compute modes.  PARITY: every multiply-add in fp32 FFMA (differs from the reference only by
+ * summation order).  TENSOR: the per-edge message GEMMs run on tcgen05 tensor cores
+ * (operands rounded to the tensor format, fp32 accumulation in TMEM). */
+#define BDIFF_MODE_PARITY_FP32 0
+#define BDIFF_MODE_TENSOR 1
+
+typedef struct bdiff_handle bdiff_handle;
+
+/* Dims of the denoiser; mirrors what GCPNetDynamics.__init__ derives from its five Hydra configs
+ * (src/models/components/gcpnet.py:933-1039).  Only the shipped option set is supported (GCP2,
+ * vector_gate, no frame_gate, bottleneck 4, 4 residual message GCPs, scalar message attention, one
+ * feed-forward GCP, no GCP norm / dropout, no self-conditioning); anything else -> BDIFF_EINVAL. */
+typedef struct bdiff_config {
+  int32_t num_h;          /* F: node scalar features in xh = [x(3) | h(F)] = num_atom_types + include_charges */
+  int32_t num_context;    /* len(module_cfg.conditioning): context columns appended after the time column     */
+  int32_t num_layers;     /* model_cfg.num_encoder_layers (9 QM9, 4 GEOM)                                      */
+  int32_t h_hidden;       /* model_cfg.h_hidden_dim   — must be 256                                            */
+  int32_t chi_hidden;     /* model_cfg.chi_hidden_dim — must be 32                                             */
+  int32_t e_hidden;       /* model_cfg.e_hidden_dim   (64 QM9, 16 GEOM), multiple of 4, <= 64                   */
+  int32_t xi_hidden;      /* model_cfg.xi_hidden_dim  (16 QM9, 8 GEOM), multiple of 4, <= 16                    */
+  int32_t mode;           /* BDIFF_MODE_*                                                                       */
+} bdiff_config;
+
+BDIFF_API int32_t bdiff_abi_version(void);
+
+/* Replaces: GCPNetDynamics.__init__ (gcpnet.py:933-1039) — allocates packed-weight storage. */
+BDIFF_API int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out);
+BDIFF_API void bdiff_destroy(bdiff_handle* h);
+BDIFF_API const char* bdiff_last_error(const bdiff_handle* h);   /* h may be NULL: last creation error */
+
+/* Replaces: nn.Module.load_state_dict on the reference module.  `name` is the reference parameter name
+ * relative to the denoiser (e.g. "interaction_layers.3.interaction.message_fusion.0.scalar_out.weight"),
+ * `data` a contiguous fp32 device tensor of `shape`.  The tensor is repacked (transposed to K-major,
+ * split, zero-padded) into the kernel layout immediately on `stream`; the caller may free it afterwards. */
+BDIFF_API int32_t bdiff_set_weight(bdiff_handle* h, void* stream, const char* name, const float* data,
+                         const int64_t* shape, int32_t ndim);
+/* Number of reference parameter tensors still missing (0 = ready); -errno on error. */
+BDIFF_API int32_t bdiff_weights_missing(const bdiff_handle* h);
+
+/* Replaces: GCPNetDynamics.get_fully_connected_edge_index (gcpnet.py:1054-1066) — as an implicit plan.
+ * batch_index int64[N] (sorted molecule ids, as every caller provides), mask uint8[N].  Builds the
+ * per-molecule offsets the kernels enumerate edges from; *num_edges_host receives E = sum_k nact_k^2.
+ * Synchronises `stream` (one small D2H + H2D).  Re-plan whenever batch_index / mask change. */
+BDIFF_API int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int64_t num_nodes,
+                            const int64_t* batch_index, const uint8_t* mask, int64_t* num_edges_host);
+
+/* Materialises the reference's edge_index int64[2,E] ((row,col)-sorted, self loops, masked nodes dropped)
+ * from the current plan — only for callers/tests that want it; the kernels never read it. */
+BDIFF_API int32_t bdiff_edge_index(bdiff_handle* h, void* stream, int64_t* edge_index);
+
+/* Replaces: GCPNetDynamics.forward / atom_types_and_coords_forward (gcpnet.py:1042-1052, 1069-1232).
+ * xh fp32[N,3+F], t fp32[N] (per node, the reference's t[batch_index]), context fp32[N,C] or NULL,
+ * net_out fp32[N,3+F] = [vel (CoG-free) | h_final].  xh is not modified. */
+BDIFF_API int32_t bdiff_denoise_forward(bdiff_handle* h, void* stream, const float* xh, const float* t,
+                              const float* context, float* net_out);
+
+/* Optional taps of the last forward, for parity tests: which = "f_ij" [E,9], "e" [E,e_hidden],
+ * "xi" [E,xi_hidden*3], "h" [N,256], "chi" [N,96], "x" [N,3], "fbar" [N,12], "chi_in" [N,6] (state after the
+ * last layer).  Writes the shape to rows/cols and, if dst != NULL, copies rows*cols floats to dst (device) on
+ * `stream`.  Returns BDIFF_EINVAL for unknown names. */
+BDIFF_API int32_t bdiff_debug_tap(bdiff_handle* h, void* stream, const char* which, float* dst, int64_t* rows,
+                                  int64_t* cols);
+
+/* Replaces: the arithmetic of EquivariantVariationalDiffusion.sample_p_zs_given_zt
+ * (variational_diffusion.py:1204-1278) around the denoiser call:
+ *   eps = denoiser(z, t);  mu = z/alpha_ts - c_eps*eps;  z' = mu + sigma*noise;  z'[:, :3] re-centred.
+ * noise_x fp32[N,3] and noise_h fp32[N,F] hold the two RAW randn draws of
+ * sample_combined_position_feature_noise (:795-819); masking and the centring of noise_x happen inside.
+ * z is updated in place.  coef_table: DEVICE array of rows {alpha_ts, c_eps, sigma, t_value} with
+ * c_eps = sigma2_ts/alpha_ts/sigma_t and sigma = sigma_ts*sigma_s/sigma_t; the row used is
+ * coef_table[*step_index] (step_index: DEVICE int32, or NULL for row 0), so one captured CUDA graph can be
+ * replayed for every step while the host only bumps the device counter. */
+BDIFF_API int32_t bdiff_reverse_step(bdiff_handle* h, void* stream, float* z, const float* context,
+                                     const float* noise_x, const float* noise_h, const float* coef_table,
+                                     const int32_t* step_index);
+
+/* Replaces: sample_p_xh_given_z0 up to the normal sample (variational_diffusion.py:840-885):
+ *   eps = denoiser(z0, 0);  xh = (1/alpha0)*(z0 - sigma0*eps) + sigma_x*noise (noise masked, x-part centred).
+ * coef = {1/alpha0, sigma0, sigma_x, 0} (device).  Writes xh fp32[N,3+F]. */
+BDIFF_API int32_t bdiff_decode_z0(bdiff_handle* h, void* stream, const float* z0, const float* context,
+                                  const float* noise_x, const float* noise_h, const float* coef, float* xh);
+
+/* Masks two raw randn draws and centres the x-part per molecule (variational_diffusion.py:795-819): z_T. */
+BDIFF_API int32_t bdiff_center_noise(bdiff_handle* h, void* stream, const float* noise_x, const float* noise_h,
+                                     float* z);
+
+/* Counters for bench.py: kernels launched by this handle since creation. */
+BDIFF_API int64_t bdiff_launch_count(const bdiff_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDIFF_H_ */
