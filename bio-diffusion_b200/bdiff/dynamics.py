@@ -22,6 +22,14 @@ from . import _lib
 from .config import DenoiserConfig, parameter_shapes
 
 
+def _version(t: torch.Tensor) -> int:
+    """Version counter of a tensor; inference tensors (the reference samples under torch.inference_mode) have none."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 class _Node(nn.Module):
     """Anonymous container used to reproduce the reference's dotted parameter names."""
 
@@ -97,7 +105,7 @@ class GCPNetDynamicsB200(nn.Module):
 
     def sync_weights(self, force: bool = False) -> None:
         """Repack the module's parameters into the kernel layout (bdiff_set_weight per tensor)."""
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple((p.data_ptr(), _version(p)) for p in self.parameters())
         if not force and key == self._weights_key:
             return
         lib = _lib.load()
@@ -119,7 +127,7 @@ class GCPNetDynamicsB200(nn.Module):
 
     def plan(self, batch_index: torch.Tensor, mask: torch.Tensor, num_mols: Optional[int] = None) -> Tuple[int, int, int]:
         """Build (or reuse) the implicit edge plan for (batch_index, mask): replaces get_fully_connected_edge_index."""
-        key = (batch_index.data_ptr(), batch_index._version, mask.data_ptr(), mask._version, batch_index.shape[0])
+        key = (batch_index.data_ptr(), _version(batch_index), mask.data_ptr(), _version(mask), batch_index.shape[0])
         if key == self._plan_key:
             return self._plan_info
         if not batch_index.is_cuda:
@@ -196,6 +204,26 @@ class GCPNetDynamicsB200(nn.Module):
         num_mols = getattr(batch, "num_graphs", None)
         net_out = self.denoise(batch.batch, batch.mask, xh, t, ctx, num_mols if isinstance(num_mols, int) else None)
         return batch, net_out
+
+    def profile_forward(self, batch_index, mask, xh, t, context=None, num_mols=None):
+        """One eager forward with CUDA events around every kernel class (inside the library, on the launch
+        stream).  Returns ({class: milliseconds}, net_out).  Synchronises; for bench.py's roofline block."""
+        lib = _lib.load()
+        self.sync_weights()
+        _, n, _ = self.plan(batch_index, mask, num_mols)
+        xh_c = xh.detach().to(torch.float32).contiguous()
+        t_c = t.detach().to(torch.float32).reshape(-1).contiguous()
+        ctx_ptr = None
+        if self.cfg.num_context:
+            ctx_c = context.detach().to(torch.float32).reshape(n, self.cfg.num_context).contiguous()
+            ctx_ptr = C.c_void_p(ctx_c.data_ptr())
+        out = torch.empty_like(xh_c)
+        ms = (C.c_float * 8)()
+        _lib.check(self._handle, lib.bdiff_profile_forward(
+            self._handle, self._stream(), C.c_void_p(xh_c.data_ptr()), C.c_void_p(t_c.data_ptr()), ctx_ptr,
+            C.c_void_p(out.data_ptr()), ms), "bdiff_profile_forward")
+        names = ("prep", "edge_embed", "node_embed", "edge_message", "node_update", "finalize", "total")
+        return {k: float(ms[i]) for i, k in enumerate(names)}, out
 
     def launch_count(self) -> int:
         return int(_lib.load().bdiff_launch_count(self._handle)) if self._handle is not None else 0

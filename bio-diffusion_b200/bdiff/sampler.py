@@ -30,6 +30,7 @@ class GCDMSampler:
         self._graph_key = None
         self._graph = None
         self._static = None
+        self.kernel_launches = 0     # libbdiff kernels launched (or replayed from the graph) by sample()
 
     # -------------------------------------------------------------------------------------------- helpers
     def _device(self) -> torch.device:
@@ -133,6 +134,9 @@ class GCDMSampler:
                 self._reverse_step(st, ctx_ptr)
                 st["step"].add_(1)
 
+        # one forward = prep, node_frames, edge_embed, node_embed, L x (edge_message, node_update), finalize
+        per_forward = 5 + 2 * cfg.num_layers
+        self.kernel_launches += 1 + steps * (per_forward + 1) + (per_forward + 1)
         # p(x, h | z_0)  (variational_diffusion.py:1378-1387, 840-907)
         z0 = st["z"].clone() if return_z0 else None
         draw(st["nx"], st["nh"])
@@ -158,6 +162,33 @@ class GCDMSampler:
         parts[0] = x
         out = torch.cat(parts, dim=-1)
         return (out, batch_index, mask, z0) if return_z0 else (out, batch_index, mask)
+
+    @torch.inference_mode()
+    def reverse_step_once(self, z: torch.Tensor, row: int, steps: int, batch_index: torch.Tensor,
+                          mask: torch.Tensor, noise_x: torch.Tensor, noise_h: torch.Tensor,
+                          context: Optional[torch.Tensor] = None, num_mols: Optional[int] = None) -> torch.Tensor:
+        """One p(z_s | z_t) step from a given z (row `row` of the coefficient table for a `steps`-step chain):
+        sample_p_zs_given_zt, variational_diffusion.py:1204-1278.  Used by teacher-forced parity tests."""
+        dev = z.device
+        self.net.sync_weights()
+        self.net.plan(batch_index, mask, num_mols)
+        lib = _lib.load()
+        h = self.net._handle
+        coef = step_coefficient_table(self.gamma, steps).to(dev)
+        idx = torch.tensor(row, dtype=torch.int32, device=dev)
+        zz = z.detach().to(torch.float32).clone().contiguous()
+        nx = noise_x.to(torch.float32).contiguous()
+        nh = noise_h.to(torch.float32).contiguous()
+        ctx_ptr = None
+        if self.cfg.num_context:
+            ctx = context.to(torch.float32).contiguous()
+            ctx_ptr = C.c_void_p(ctx.data_ptr())
+        _lib.check(h, lib.bdiff_reverse_step(h, self.net._stream(), C.c_void_p(zz.data_ptr()), ctx_ptr,
+                                             C.c_void_p(nx.data_ptr()), C.c_void_p(nh.data_ptr()),
+                                             C.c_void_p(coef.data_ptr()), C.c_void_p(idx.data_ptr())),
+                   "bdiff_reverse_step")
+        torch.cuda.current_stream().synchronize()
+        return zz
 
     @torch.inference_mode()
     def sample_from_host(self, num_nodes_host: torch.Tensor, context_host: Optional[torch.Tensor] = None,

@@ -434,7 +434,8 @@ int32_t bdiff_edge_index(bdiff_handle* h, void* stream, int64_t* edge_index) {
 }
 
 static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, const float* t_nodes,
-                            const float* coef_table, const int* step_ptr, const float* context, float* net_out) {
+                            const float* coef_table, const int* step_ptr, const float* context, float* net_out,
+                            std::vector<cudaEvent_t>* ev = nullptr) {
   if (!h->have_plan) return h->fail(BDIFF_ESTATE, "bdiff_plan_topology has not been called");
   if (bdiff_weights_missing(h) != 0) {
     for (auto& kv : h->seen)
@@ -444,20 +445,56 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
   const Plan& p = h->plan;
   const Dims& d = h->d;
   const Work& w = h->work;
+  auto mark = [&]() {
+    if (!ev) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev->push_back(e);
+  };
+  mark();
   launch_prep(st, p, d, xh, t_nodes, coef_table, step_ptr, context, w);
+  mark();
   launch_edge_embed(st, p, d, h->embed, w);
+  mark();
   launch_node_embed(st, p, d, h->embed, h->layers[0], w);
+  mark();
   h->launches += 4;
   for (int l = 0; l < d.L; ++l) {
     launch_edge_message(st, p, d, h->layers[l], w);
+    mark();
     const bool last = (l == d.L - 1);
     launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);
+    mark();
     h->launches += 2;
   }
   launch_finalize(st, p, d, w, net_out);
+  mark();
   h->launches += 1;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "forward: %s", cudaGetErrorString(e));
+}
+
+int32_t bdiff_profile_forward(bdiff_handle* h, void* stream, const float* xh, const float* t, const float* context,
+                              float* net_out, float* ms_host) {
+  if (!h || !xh || !t || !net_out || !ms_host) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev;
+  int32_t rc = forward_impl(h, st, xh, t, nullptr, nullptr, context, net_out, &ev);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == BDIFF_OK && e != cudaSuccess) rc = h->fail(BDIFF_ECUDA, "profile sync: %s", cudaGetErrorString(e));
+  for (int i = 0; i < 8; ++i) ms_host[i] = 0.f;
+  if (rc == BDIFF_OK) {
+    auto dt = [&](size_t a, size_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[a], ev[b]); return ms; };
+    const int L = h->d.L;
+    ms_host[0] = dt(0, 1); ms_host[1] = dt(1, 2); ms_host[2] = dt(2, 3);
+    for (int l = 0; l < L; ++l) { ms_host[3] += dt(3 + 2 * l, 4 + 2 * l); ms_host[4] += dt(4 + 2 * l, 5 + 2 * l); }
+    ms_host[5] = dt(3 + 2 * L, 4 + 2 * L);
+    ms_host[6] = dt(0, 4 + 2 * L);
+    ms_host[7] = (float)L;
+  }
+  for (cudaEvent_t x : ev) cudaEventDestroy(x);
+  return rc;
 }
 
 int32_t bdiff_denoise_forward(bdiff_handle* h, void* stream, const float* xh, const float* t, const float* context,

@@ -95,6 +95,13 @@ BDIFF_API int32_t bdiff_edge_index(bdiff_handle* h, void* stream, int64_t* edge_
 BDIFF_API int32_t bdiff_denoise_forward(bdiff_handle* h, void* stream, const float* xh, const float* t,
                               const float* context, float* net_out);
 
+/* Same as bdiff_denoise_forward, but records CUDA events on `stream` around every kernel class and, after
+ * synchronising the stream, writes milliseconds to ms_host[0..6] = {prep+node_frames, edge_embed, node_embed,
+ * edge_message (sum over layers), node_update (sum over layers), finalize, whole forward}; ms_host[7] = number
+ * of edge_message launches.  Measurement hook for bench.py's roofline block (not on the product path). */
+BDIFF_API int32_t bdiff_profile_forward(bdiff_handle* h, void* stream, const float* xh, const float* t,
+                                        const float* context, float* net_out, float* ms_host);
+
 /* Optional taps of the last forward, for parity tests: which = "f_ij" [E,9], "e" [E,e_hidden],
  * "xi" [E,xi_hidden*3], "h" [N,256], "chi" [N,96], "x" [N,3], "fbar" [N,12], "chi_in" [N,6] (state after the
  * last layer).  Writes the shape to rows/cols and, if dst != NULL, copies rows*cols floats to dst (device) on

@@ -3,7 +3,7 @@
 The fixtures were produced by the unmodified reference (tests/golden/make_golden.py); the weights are
 regenerated from their seed and checksummed first.  Tolerances: integer work bit-exact; floating
 point max-abs <= 2e-5 * max(1, |ref|_max) per forward (the measured fp32-vs-fp64 floor is ~1e-6,
-SURVEY.md §8c), chains 1e-3 relative.
+SURVEY.md §8c), chains 1e-4 relative (chain fixtures use 0.5-scaled weights: well-conditioned regime).
 """
 import pytest
 import torch
@@ -16,7 +16,7 @@ FWD_CASES = ["qm9_small_masked", "qm9_tiny_sizes", "qm9_b4_n19", "qm9_cond", "ge
 
 def weights_for(fx):
     cfg = O.config_named(fx["config"])
-    sd = O.random_state_dict(cfg, fx["weight_seed"])
+    sd = O.random_state_dict(cfg, fx["weight_seed"], scale=fx.get("weight_scale", 1.0))
     tot = sum(float(v.double().sum()) for v in sd.values())
     sq = sum(float((v.double() ** 2).sum()) for v in sd.values())
     assert abs(tot - float(fx["weight_checksum"][0])) < 1e-6 * max(1.0, abs(tot))
@@ -69,11 +69,11 @@ def test_chain_matches_reference(name):
     out, bi, mask, z0 = O.sample_chain(sd, cfg, torch.tensor(fx["sizes"]), lambda s: torch.randn(s),
                                        num_timesteps=fx["steps"], context=fx["context"], return_z0=True)
     rel = (z0 - fx["z_0"]).abs().max().item() / fx["z_0"].abs().max().item()
-    assert rel < 1e-3
+    assert rel < 1e-4
     a = cfg.num_atom_types
     assert torch.equal(out[:, 3:3 + a], fx["out"][:, 3:3 + a])
     relx = (out[:, :3] - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
-    assert relx < 1e-3
+    assert relx < 1e-4
 
 
 def test_se3_equivariance_of_oracle():
