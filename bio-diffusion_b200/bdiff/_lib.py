@@ -33,6 +33,8 @@ PROTOTYPES = {
     "bdiff_last_error": (C.c_char_p, [C.c_void_p]),
     "bdiff_set_weight": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "bdiff_weights_missing": (C.c_int32, [C.c_void_p]),
+    "bdiff_prepare": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bdiff_selftest_umma": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bdiff_plan_topology": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_int64)]),
     "bdiff_edge_index": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -123,6 +123,7 @@ class GCPNetDynamicsB200(nn.Module):
         missing = lib.bdiff_weights_missing(h)
         if missing != 0:
             raise _lib.BdiffError(f"{missing} parameter tensors were not set")
+        _lib.check(h, lib.bdiff_prepare(h, st), "bdiff_prepare")
         self._weights_key = key
 
     def plan(self, batch_index: torch.Tensor, mask: torch.Tensor, num_mols: Optional[int] = None) -> Tuple[int, int, int]:

@@ -66,8 +66,11 @@ struct bdiff_handle {
   DevBuf eps_buf;      // [N,3+F] denoiser output inside reverse_step / decode
   DevBuf tu_buf;       // uniform t scalar
 
-  // tensor-core path state (bdiff_edge_tc.cu)
-  void* tc_state = nullptr;
+  // tensor-core path state (bdiff_edge_tc.cu): per-layer pre-swizzled bf16 weight blobs
+  DevBuf tc_blob;
+  size_t tc_layer_bytes = 0;
+  bool tc_dirty = true;
+  int num_sms = 148;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -306,7 +309,19 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
     gcp_names(h->seen, p + "feedforward_network.0.", true, true);
     gcp_names(h->seen, p + "node_position_update_gcp.", false, true);
   }
+  h->num_sms = prop.multiProcessorCount;
   cudaError_t e = configure_kernels();
+  if (e == cudaSuccess && cfg->mode == BDIFF_MODE_TENSOR) {
+    if (!tc_supported(d.Ed, d.Xd)) {
+      g_create_error = "tensor mode supports (e_hidden, xi_hidden) in {(64,16), (16,8)} only";
+      cudaFree(h->wbuf);
+      delete h;
+      return BDIFF_EINVAL;
+    }
+    e = tc_configure();
+    h->tc_layer_bytes = tc_blob_bytes(d.Ed, d.Xd);
+    if (e == cudaSuccess) e = h->tc_blob.ensure(h->tc_layer_bytes * d.L);
+  }
   if (e != cudaSuccess) {
     g_create_error = std::string("configure_kernels: ") + cudaGetErrorString(e);
     cudaFree(h->wbuf);
@@ -320,7 +335,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
 void bdiff_destroy(bdiff_handle* h) {
   if (!h) return;
   if (h->wbuf) cudaFree(h->wbuf);
-  h->plan_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release();
+  h->plan_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release();
   delete h;
 }
 
@@ -344,7 +359,37 @@ int32_t bdiff_set_weight(bdiff_handle* h, void* stream, const char* name, const 
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "pack '%s': %s", name, cudaGetErrorString(e));
   it->second = true;
+  h->tc_dirty = true;
   return BDIFF_OK;
+}
+
+static void tc_prepare(bdiff_handle* h, cudaStream_t st) {
+  if (h->cfg.mode != BDIFF_MODE_TENSOR || !h->tc_dirty) return;
+  for (int l = 0; l < h->d.L; ++l) {
+    launch_tc_pack(st, h->layers[l], h->d, static_cast<unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes);
+    h->launches++;
+  }
+  h->tc_dirty = false;
+}
+
+int32_t bdiff_prepare(bdiff_handle* h, void* stream) {
+  if (!h) return BDIFF_EINVAL;
+  if (bdiff_weights_missing(h) != 0) return h->fail(BDIFF_ESTATE, "%d parameters not set", bdiff_weights_missing(h));
+  tc_prepare(h, static_cast<cudaStream_t>(stream));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "prepare: %s", cudaGetErrorString(e));
+}
+
+int32_t bdiff_selftest_umma(void* stream, const float* A, const float* W, float* C) {
+  if (!A || !W || !C) return BDIFF_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tc_configure() != cudaSuccess) return BDIFF_ECUDA;
+  void* img = nullptr;
+  if (cudaMalloc(&img, 2 * 320 * 128) != cudaSuccess) return BDIFF_ENOMEM;
+  launch_umma_selftest(st, A, W, static_cast<unsigned char*>(img), C);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(img);
+  return e == cudaSuccess ? BDIFF_OK : BDIFF_ECUDA;
 }
 
 int32_t bdiff_weights_missing(const bdiff_handle* h) {
@@ -452,6 +497,8 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
     cudaEventRecord(e, st);
     ev->push_back(e);
   };
+  tc_prepare(h, st);
+  const bool tensor = h->cfg.mode == BDIFF_MODE_TENSOR;
   mark();
   launch_prep(st, p, d, xh, t_nodes, coef_table, step_ptr, context, w);
   mark();
@@ -461,7 +508,11 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
   mark();
   h->launches += 4;
   for (int l = 0; l < d.L; ++l) {
-    launch_edge_message(st, p, d, h->layers[l], w);
+    if (tensor)
+      launch_edge_message_tc(st, p, d, h->layers[l],
+                             static_cast<const unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes, w, h->num_sms);
+    else
+      launch_edge_message(st, p, d, h->layers[l], w);
     mark();
     const bool last = (l == d.L - 1);
     launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);

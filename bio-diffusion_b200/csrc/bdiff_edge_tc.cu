@@ -1,0 +1,662 @@
+// bdiff_edge_tc.cu — tensor-core (tcgen05 / TMEM / TMA-bulk) version of the fused edge pass.
+//
+// Same math as k_edge_message (gcpnet.py:676-737: 4 residual GCP2s on the per-edge message, attention gate,
+// segmented row-sum) but the dense scalar GEMMs run on the 5th-gen tensor cores:
+//   * persistent CTAs (one per SM), tile = 128 consecutive edges = the 128 TMEM lanes (thread t <-> edge t);
+//   * A operand = the running scalar message m.s as bf16 in shared memory (K-major, 128B-swizzled), written by
+//     the epilogue warps; B operand = pre-swizzled bf16 weight K-blocks streamed from L2 by TMA bulk copies
+//     through a 2-stage mbarrier ring; fp32 accumulators in TMEM;
+//   * the vector gate  sigmoid(Wg_k silu(S_k) + b)  is folded into the surrounding GEMMs as extra N=32 column
+//     groups using  Wg_k new_k = Wg_k m_k - Wg_k m_{k-1}  (second term issued with the A-negate bit), so the
+//     only A operand ever needed is m.s;
+//   * the equivariant vector channel (32x3 per edge) lives in TMEM scratch columns of the owning lane and is
+//     updated with thread-local FMAs (weights broadcast from shared memory);
+//   * warp roles: warps 0-3 epilogue/compute, warp 4 TMA producer (+TMEM allocator), warp 5 MMA issuer.
+#include "bdiff_kernels.h"
+#include "bdiff_tc.cuh"
+
+namespace bdiff {
+
+constexpr int TC_THREADS = 192;
+constexpr int TMT = 128;                 // edges per tile
+constexpr int X_BLOCK = TMT * 128;       // bytes of one A K-block (64 bf16 per row)
+constexpr int RING_STAGE = 320 * 128;    // bytes of the largest weight chunk (320 rows x 64 bf16)
+// TMEM column map (512 columns allocated)
+constexpr int TM_S = 0, TM_U0 = 256, TM_U1 = 288, TM_MV = 320, TM_VD0 = 416;
+
+__host__ __device__ inline int tc_nc0(int Ed, int Xd) {          // weight chunks of message GCP 0
+  const int k0raw = Ed + (64 + Xd) / 4 + 9;
+  return ((k0raw + 15) / 16 + 3) / 4;
+}
+size_t tc_blob_bytes(int Ed, int Xd) {
+  return (size_t)tc_nc0(Ed, Xd) * 256 * 128 + 3 * (4 * (size_t)RING_STAGE + 256 * 128) + 4 * 32 * 128;
+}
+
+// ---------------------------------------------------------------------------------------------- weight blob
+// Builds the per-layer bf16 blob: a sequence of K-blocks [rows][64] in the 128B-swizzled shared-memory image,
+// in the exact order the producer streams them:  G0 chunks | for k=1..3: 4 x [W_k | Wg_{k-1} | Wg_k] , W_k tail |
+// 4 x Wg_3.
+__global__ void k_tc_pack_layer(LayerW lw, Dims d, unsigned char* __restrict__ blob) {
+  const int nc0 = tc_nc0(d.Ed, d.Xd);
+  const long long total_rows = (long long)nc0 * 256 + 3 * (4 * 320 + 256) + 4 * 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_rows * 64) return;
+  long long rowg = idx / 64;
+  const int kc = (int)(idx - rowg * 64);
+  size_t base = 0;
+  float v = 0.f;
+  int r = 0;
+  if (rowg < (long long)nc0 * 256) {
+    const int j = (int)(rowg / 256);
+    r = (int)(rowg - (long long)j * 256);
+    base = (size_t)j * 256 * 128;
+    const int kk = j * 64 + kc;
+    v = kk < d.K0 ? lw.W0e[(size_t)kk * 256 + r] : 0.f;
+  } else {
+    rowg -= (long long)nc0 * 256;
+    base = (size_t)nc0 * 256 * 128;
+    const long long per_k = 4 * 320 + 256;
+    if (rowg < 3 * per_k) {
+      const int k = (int)(rowg / per_k);           // message GCP k+1
+      long long rr = rowg - k * per_k;
+      base += (size_t)k * per_k * 128;
+      if (rr < 4 * 320) {
+        const int j = (int)(rr / 320);
+        r = (int)(rr - j * 320);
+        base += (size_t)j * 320 * 128;
+        const int kk = j * 64 + kc;
+        if (r < 256) v = lw.Wk[k][(size_t)kk * 256 + r];
+        else if (r < 288) v = (k == 0 ? lw.Wg0 : lw.Wgk[k - 1])[(size_t)kk * 32 + (r - 256)];
+        else v = lw.Wgk[k][(size_t)kk * 32 + (r - 288)];
+      } else {
+        r = (int)(rr - 4 * 320);
+        base += (size_t)4 * 320 * 128;
+        const int kk = 256 + kc;
+        v = kk < kKM ? lw.Wk[k][(size_t)kk * 256 + r] : 0.f;
+      }
+    } else {
+      long long rr = rowg - 3 * per_k;
+      base += (size_t)3 * per_k * 128;
+      const int j = (int)(rr / 32);
+      r = (int)(rr - j * 32);
+      base += (size_t)j * 32 * 128;
+      v = lw.Wgk[2][(size_t)(j * 64 + kc) * 32 + r];
+    }
+  }
+  *reinterpret_cast<__nv_bfloat16*>(blob + base + sw128_offset(r, kc)) = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------ self test
+// C[128][320] = A[128][128] . W[320][128]^T with the exact machinery of the edge kernel: swizzled bf16 A written
+// by threads, W image fetched by a TMA bulk copy, three MMAs per K step (N=256 | N=32 | N=32 with A negated),
+// TMEM scratch round trip in column 320.  Used by tests/test_gpu_tc.py before the fused kernel is trusted.
+__global__ void __launch_bounds__(TC_THREADS, 1) k_umma_selftest(const float* __restrict__ A,
+                                                                 const unsigned char* __restrict__ wimg,
+                                                                 float* __restrict__ C) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* X = smem;                          // 2 K-blocks of A
+  unsigned char* Wb = smem + 2 * X_BLOCK;           // 2 K-blocks of W (320 rows each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wb + 2 * RING_STAGE);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);      // weights landed
+    mbar_init(&bars[1], 1);      // MMAs done
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (tid < TMT) {
+    for (int k8 = 0; k8 < 16; ++k8) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        pk[q] = pack_bf16x2(A[(size_t)tid * 128 + k8 * 8 + 2 * q], A[(size_t)tid * 128 + k8 * 8 + 2 * q + 1]);
+      const int kk = k8 * 8;
+      *reinterpret_cast<uint4*>(X + (kk / 64) * X_BLOCK + sw128_offset(tid, kk % 64)) =
+          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    fence_proxy_async();
+  }
+  if (tid == TMT) {   // warp 4 lane 0: fetch both weight K-blocks
+    mbar_expect_tx(&bars[0], 2 * RING_STAGE);
+    bulk_g2s(Wb, wimg, RING_STAGE, &bars[0]);
+    bulk_g2s(Wb + RING_STAGE, wimg + RING_STAGE, RING_STAGE, &bars[0]);
+  }
+  __syncthreads();
+  if (tid == TMT + 32) {   // warp 5 lane 0: MMA issuer
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
+                   i32n = umma_idesc_bf16(32, true);
+    for (int j = 0; j < 2; ++j)
+      for (int s = 0; s < 4; ++s) {
+        const uint64_t ad = umma_desc_sw128(smem_u32(X + j * X_BLOCK) + s * 32);
+        const uint32_t wb = smem_u32(Wb + j * RING_STAGE) + s * 32;
+        const bool acc = (j | s) > 0;
+        umma_bf16(tmem + TM_S, ad, umma_desc_sw128(wb), i256, acc);
+        umma_bf16(tmem + TM_U0, ad, umma_desc_sw128(wb + 256 * 128), i32, acc);
+        umma_bf16(tmem + TM_U1, ad, umma_desc_sw128(wb + 288 * 128), i32n, acc);
+      }
+    umma_commit(&bars[1]);
+  }
+  if (tid < TMT) {
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    float sc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = (float)(tid * 8 + i);
+    tmem_st8(tl + TM_MV, sc);
+    for (int c0 = 0; c0 < 320; c0 += 32) {
+      float v[32];
+      tmem_ld32(tl + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) C[(size_t)tid * 328 + c0 + i] = v[i];
+    }
+    float back[8];
+    tmem_ld8(tl + TM_MV, back);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) C[(size_t)tid * 328 + 320 + i] = back[i];
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+  (void)lane;
+}
+
+// [320][128] fp32 -> two swizzled bf16 K-blocks of 320 rows (the self test's weight image)
+__global__ void k_selftest_pack(const float* __restrict__ W, unsigned char* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 320 * 128) return;
+  const int r = idx / 128, k = idx - r * 128;
+  *reinterpret_cast<__nv_bfloat16*>(img + (k / 64) * RING_STAGE + sw128_offset(r, k % 64)) =
+      __float2bfloat16_rn(W[idx]);
+}
+
+// --------------------------------------------------------------------------------------------- fused kernel
+struct SmallW {            // fp32 copies of the thread-local (vector channel) weights, broadcast-read
+  float Wd0x[16 * 20];     // [Xd][hid0]
+  float Wf0x[16 * 3];      // [Xd][3]
+  float Wu0[20 * 32];      // [hid0][32]
+  float Wdk[3][32 * 8];    // [32][8]
+  float Wfk[3][32 * 3];    // [32][3]
+  float Wuk[3][8 * 32];    // [8][32]
+  float bg[4][32];
+  float bk[3][256];
+  float wa[256];
+  float ba[4];
+};
+
+struct TcSmemTail {
+  float sT[TMT][33];       // transpose buffer of the final segmented reduction (32 columns at a time)
+  SmallW sw;
+  int sRow[TMT], sCol[TMT], sB[TMT], sNa[TMT];
+  uint64_t full[2], empty[2], a_ready, d_full;
+  uint32_t tmem_ptr;
+};
+
+constexpr size_t TC_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)RING_STAGE + sizeof(TcSmemTail) + 1024;
+
+__device__ __forceinline__ void x_store8(unsigned char* X, int r, int kk, const float* v) {   // kk % 8 == 0
+  *reinterpret_cast<uint4*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63)) =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void x_load8(const unsigned char* X, int r, int kk, float* v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63));
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y;
+}
+
+// Gate of the previous GCP from TMEM (U), vector-message update in TMEM scratch, and vector_down /
+// vector_down_frames of the NEXT GCP accumulated on the fly.  HP = hidden dim of the previous GCP.
+template <int HP, bool FIRST, bool LAST>
+__device__ __forceinline__ void gate_update(uint32_t tl, int ucol, const float* __restrict__ vdp,
+                                            const float* __restrict__ Wu, const float* __restrict__ bgp,
+                                            const float* __restrict__ Wdn, const float* __restrict__ Wfn,
+                                            float* __restrict__ vdn, float* __restrict__ vdfn) {
+  if (!LAST) {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) vdn[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) vdfn[i] = 0.f;
+  }
+  for (int oc = 0; oc < 4; ++oc) {
+    float u[8], mv[24];
+    tmem_ld8(tl + ucol + oc * 8, u);
+    if (!FIRST) {
+      tmem_ld8(tl + TM_MV + oc * 24, mv);
+      tmem_ld8(tl + TM_MV + oc * 24 + 8, mv + 8);
+      tmem_ld8(tl + TM_MV + oc * 24 + 16, mv + 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = oc * 8 + j;
+      const float g = sigmoid_fast(u[j] + bgp[o]);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int h = 0; h < HP; ++h) {
+        const float wu = Wu[h * 32 + o];
+        s0 = fmaf(wu, vdp[h * 3 + 0], s0);
+        s1 = fmaf(wu, vdp[h * 3 + 1], s1);
+        s2 = fmaf(wu, vdp[h * 3 + 2], s2);
+      }
+      if (FIRST) { mv[j * 3] = s0 * g; mv[j * 3 + 1] = s1 * g; mv[j * 3 + 2] = s2 * g; }
+      else { mv[j * 3] = fmaf(s0, g, mv[j * 3]); mv[j * 3 + 1] = fmaf(s1, g, mv[j * 3 + 1]); mv[j * 3 + 2] = fmaf(s2, g, mv[j * 3 + 2]); }
+    }
+    tmem_st8(tl + TM_MV + oc * 24, mv);
+    tmem_st8(tl + TM_MV + oc * 24 + 8, mv + 8);
+    tmem_st8(tl + TM_MV + oc * 24 + 16, mv + 16);
+    if (!LAST) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = oc * 8 + j;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const float wd = Wdn[c * 8 + h];
+          vdn[h * 3 + 0] = fmaf(wd, mv[j * 3 + 0], vdn[h * 3 + 0]);
+          vdn[h * 3 + 1] = fmaf(wd, mv[j * 3 + 1], vdn[h * 3 + 1]);
+          vdn[h * 3 + 2] = fmaf(wd, mv[j * 3 + 2], vdn[h * 3 + 2]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          const float wf = Wfn[c * 3 + ch];
+          vdfn[ch * 3 + 0] = fmaf(wf, mv[j * 3 + 0], vdfn[ch * 3 + 0]);
+          vdfn[ch * 3 + 1] = fmaf(wf, mv[j * 3 + 1], vdfn[ch * 3 + 1]);
+          vdfn[ch * 3 + 2] = fmaf(wf, mv[j * 3 + 2], vdfn[ch * 3 + 2]);
+        }
+      }
+    }
+  }
+}
+
+// [vn(8) | q(9) | 0...] of the next GCP -> A K-block 4, columns 0..31
+__device__ __forceinline__ void write_extra_block(unsigned char* X, int r, const float* vd, const float* vdf,
+                                                  const float* f) {
+  float a[32];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) a[h] = safe_norm3(vd[h * 3], vd[h * 3 + 1], vd[h * 3 + 2]);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax)
+      a[8 + ch * 3 + ax] = f[ax * 3] * vdf[ch * 3] + f[ax * 3 + 1] * vdf[ch * 3 + 1] + f[ax * 3 + 2] * vdf[ch * 3 + 2];
+#pragma unroll
+  for (int i = 17; i < 32; ++i) a[i] = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) x_store8(X, r, 256 + q * 8, a + q * 8);
+}
+
+template <int ED, int XD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    k_edge_message_tc(Plan p, LayerW lw, const unsigned char* __restrict__ blob, Work w, int ntiles) {
+  constexpr int HID0 = (64 + XD) / 4;
+  constexpr int K0RAW = ED + HID0 + 9;
+  constexpr int K0S = (K0RAW + 15) / 16;
+  constexpr int NC0 = (K0S + 3) / 4;
+  static_assert(HID0 * 3 <= 64 && HID0 + 9 <= 32, "scratch layout");
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* X = smem;
+  unsigned char* ring = smem + 5 * X_BLOCK;
+  TcSmemTail& T = *reinterpret_cast<TcSmemTail*>(ring + 2 * RING_STAGE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&T.full[0], 1); mbar_init(&T.full[1], 1);
+    mbar_init(&T.empty[0], 1); mbar_init(&T.empty[1], 1);
+    mbar_init(&T.a_ready, TMT);
+    mbar_init(&T.d_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(&T.tmem_ptr, 512);
+  // small weights -> shared memory (all threads)
+  {
+    SmallW& s = T.sw;
+    for (int i = tid; i < XD * HID0; i += TC_THREADS) s.Wd0x[i] = lw.Wd0x[i];
+    for (int i = tid; i < XD * 3; i += TC_THREADS) s.Wf0x[i] = lw.Wf0x[i];
+    for (int i = tid; i < HID0 * 32; i += TC_THREADS) s.Wu0[i] = lw.Wu0[i];
+    for (int k = 0; k < 3; ++k) {
+      for (int i = tid; i < 256; i += TC_THREADS) { s.Wdk[k][i] = lw.Wdk[k][i]; s.Wuk[k][i] = lw.Wuk[k][i]; s.bk[k][i] = lw.bk[k][i]; }
+      for (int i = tid; i < 96; i += TC_THREADS) s.Wfk[k][i] = lw.Wfk[k][i];
+      for (int i = tid; i < 32; i += TC_THREADS) s.bg[k + 1][i] = lw.bgk[k][i];
+    }
+    for (int i = tid; i < 32; i += TC_THREADS) s.bg[0][i] = lw.bg0[i];
+    for (int i = tid; i < 256; i += TC_THREADS) s.wa[i] = lw.wa[i];
+    if (tid == 0) s.ba[0] = lw.ba[0];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = T.tmem_ptr;
+
+  if (warp == 4) {
+    // ===================================================================== TMA producer (one lane)
+    if (lane == 0) {
+      uint32_t ci = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        size_t off = 0;
+        auto push = [&](uint32_t bytes) {
+          const uint32_t s = ci & 1;
+          mbar_wait(&T.empty[s], ((ci >> 1) & 1) ^ 1);
+          mbar_expect_tx(&T.full[s], bytes);
+          bulk_g2s(ring + s * RING_STAGE, blob + off, bytes, &T.full[s]);
+          off += bytes;
+          ++ci;
+        };
+        for (int j = 0; j < NC0; ++j) push(256 * 128);
+        for (int k = 0; k < 3; ++k) {
+          for (int j = 0; j < 4; ++j) push(320 * 128);
+          push(256 * 128);
+        }
+        for (int j = 0; j < 4; ++j) push(32 * 128);
+      }
+    }
+  } else if (warp == 5) {
+    // ======================================================================= MMA issuer (one lane)
+    if (lane == 0) {
+      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
+                     i32n = umma_idesc_bf16(32, true);
+      const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
+      uint32_t ci = 0, pa = 0;
+      auto wait_a = [&]() { mbar_wait(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
+      auto wait_w = [&]() -> uint32_t {
+        const uint32_t s = ci & 1;
+        mbar_wait(&T.full[s], (ci >> 1) & 1);
+        tc_fence_after();
+        return raddr + s * RING_STAGE;
+      };
+      auto done_w = [&]() { umma_commit(&T.empty[ci & 1]); ++ci; };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // ---- G0: S = [e | vn0 | q0] . W0e^T
+        wait_a();
+        for (int j = 0; j < NC0; ++j) {
+          const uint32_t wb = wait_w();
+          const int ns = min(4, K0S - 4 * j);
+          for (int s = 0; s < ns; ++s)
+            umma_bf16(tmem + TM_S, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256,
+                      (j | s) > 0);
+          done_w();
+        }
+        umma_commit(&T.d_full);
+        for (int k = 1; k <= 3; ++k) {
+          // ---- G(k)a: S = m_{k-1} . W_k[:, :256]^T ;  U[(k-1)&1] += Wg_{k-1} m_{k-1} ;  U[k&1] = -Wg_k m_{k-1}
+          wait_a();
+          const uint32_t up = tmem + (((k - 1) & 1) ? TM_U1 : TM_U0), un = tmem + ((k & 1) ? TM_U1 : TM_U0);
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t wb = wait_w();
+            for (int s = 0; s < 4; ++s) {
+              const uint64_t ad = umma_desc_sw128(xaddr + j * X_BLOCK + s * 32);
+              const bool acc = (j | s) > 0;
+              umma_bf16(tmem + TM_S, ad, umma_desc_sw128(wb + s * 32), i256, acc);
+              umma_bf16(up, ad, umma_desc_sw128(wb + 256 * 128 + s * 32), i32, k == 1 ? acc : true);
+              umma_bf16(un, ad, umma_desc_sw128(wb + 288 * 128 + s * 32), i32n, acc);
+            }
+            done_w();
+          }
+          umma_commit(&T.d_full);
+          // ---- G(k)b: S += [vn_k | q_k] . W_k[:, 256:288]^T
+          wait_a();
+          {
+            const uint32_t wb = wait_w();
+            for (int s = 0; s < 2; ++s)
+              umma_bf16(tmem + TM_S, umma_desc_sw128(xaddr + 4 * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256,
+                        true);
+            done_w();
+          }
+          umma_commit(&T.d_full);
+        }
+        // ---- G4: U1 += Wg_3 m_3
+        wait_a();
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t wb = wait_w();
+          for (int s = 0; s < 4; ++s)
+            umma_bf16(tmem + TM_U1, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i32,
+                      true);
+          done_w();
+        }
+        umma_commit(&T.d_full);
+      }
+    }
+  } else {
+    // ============================================================ epilogue / compute warps (thread t <-> edge t)
+    const int r = tid;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const SmallW& sw = T.sw;
+    uint32_t pd = 0;
+    auto wait_d = [&]() { mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); };
+    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); };
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long g = (long long)tile * TMT + r;
+      int row = -1, col = -1, b = 0, na = 0;
+      if (g < p.E) {
+        const int k = find_mol(p.edge_off, p.B, g);
+        const int loc = (int)(g - p.edge_off[k]);
+        const int a0 = p.act_off[k];
+        na = p.act_off[k + 1] - a0;
+        const int a = loc / na;
+        b = loc - a * na;
+        row = p.act_idx[a0 + a];
+        col = p.act_idx[a0 + b];
+      }
+      T.sRow[r] = row; T.sCol[r] = col; T.sB[r] = b; T.sNa[r] = na;
+      float f[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q) f[q] = w.frames[(size_t)g * 9 + q];
+      const float* pi = w.PI + (size_t)(row < 0 ? 0 : row) * kPStride;
+      const float* pj = w.PJ + (size_t)(col < 0 ? 0 : col) * kPStride;
+      // ---- T0: A operand of GCP 0 = [e | vn0 | q0]; VD0 kept in TMEM scratch for the vector_up of GCP 0
+      {
+        const float* er = w.e + (size_t)g * ED;
+#pragma unroll
+        for (int c8 = 0; c8 < ED; c8 += 8) {
+          const float4 a = *reinterpret_cast<const float4*>(er + c8), bq = *reinterpret_cast<const float4*>(er + c8 + 4);
+          const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+          x_store8(X, r, c8, v);
+        }
+        float xi[XD * 3];
+        const float* xr = w.xi + (size_t)g * (XD * 3);
+#pragma unroll
+        for (int c4 = 0; c4 < XD * 3; c4 += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(xr + c4);
+          xi[c4] = a.x; xi[c4 + 1] = a.y; xi[c4 + 2] = a.z; xi[c4 + 3] = a.w;
+        }
+        float vd0[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) vd0[i] = 0.f;
+        float vdf0[9];
+        if (row >= 0) {
+#pragma unroll
+          for (int i = 0; i < HID0 * 3; ++i) vd0[i] = pi[kH + i] + pj[kH + i];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) vdf0[i] = pi[kH + HID0 * 3 + i] + pj[kH + HID0 * 3 + i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) vdf0[i] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < XD; ++c) {
+#pragma unroll
+          for (int h = 0; h < HID0; ++h) {
+            const float wd = sw.Wd0x[c * HID0 + h];
+            vd0[h * 3 + 0] = fmaf(wd, xi[c * 3 + 0], vd0[h * 3 + 0]);
+            vd0[h * 3 + 1] = fmaf(wd, xi[c * 3 + 1], vd0[h * 3 + 1]);
+            vd0[h * 3 + 2] = fmaf(wd, xi[c * 3 + 2], vd0[h * 3 + 2]);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            const float wf = sw.Wf0x[c * 3 + ch];
+            vdf0[ch * 3 + 0] = fmaf(wf, xi[c * 3 + 0], vdf0[ch * 3 + 0]);
+            vdf0[ch * 3 + 1] = fmaf(wf, xi[c * 3 + 1], vdf0[ch * 3 + 1]);
+            vdf0[ch * 3 + 2] = fmaf(wf, xi[c * 3 + 2], vdf0[ch * 3 + 2]);
+          }
+        }
+        float a0v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a0v[i] = 0.f;
+#pragma unroll
+        for (int h = 0; h < HID0; ++h) a0v[h] = safe_norm3(vd0[h * 3], vd0[h * 3 + 1], vd0[h * 3 + 2]);
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+          for (int ax = 0; ax < 3; ++ax)
+            a0v[HID0 + ch * 3 + ax] =
+                f[ax * 3] * vdf0[ch * 3] + f[ax * 3 + 1] * vdf0[ch * 3 + 1] + f[ax * 3 + 2] * vdf0[ch * 3 + 2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x_store8(X, r, ED + q * 8, a0v + q * 8);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tmem_st8(tl + TM_VD0 + q * 8, vd0 + q * 8);
+      }
+      publish();
+
+      // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col])
+      wait_d();
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        float v[32];
+        tmem_ld32(tl + TM_S + c0, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+          if (row >= 0) {
+            a = *reinterpret_cast<const float4*>(pi + c0 + q * 4);
+            bq = *reinterpret_cast<const float4*>(pj + c0 + q * 4);
+          }
+          v[q * 4 + 0] = silu_fast(v[q * 4 + 0] + a.x + bq.x);
+          v[q * 4 + 1] = silu_fast(v[q * 4 + 1] + a.y + bq.y);
+          v[q * 4 + 2] = silu_fast(v[q * 4 + 2] + a.z + bq.z);
+          v[q * 4 + 3] = silu_fast(v[q * 4 + 3] + a.w + bq.w);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
+      }
+      publish();
+
+      float vd[24], vdf[9];
+      float adot = 0.f;
+      for (int k = 1; k <= 3; ++k) {
+        // ---- E(k)a: gate_{k-1}, m.v update, vector_down of GCP k -> A block 4
+        wait_d();
+        if (k == 1) {
+          float vd0[64];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) tmem_ld8(tl + TM_VD0 + q * 8, vd0 + q * 8);
+          gate_update<HID0, true, false>(tl, TM_U0, vd0, sw.Wu0, sw.bg[0], sw.Wdk[0], sw.Wfk[0], vd, vdf);
+        } else {
+          float vdn[24], vdfn[9];
+          gate_update<8, false, false>(tl, ((k - 1) & 1) ? TM_U1 : TM_U0, vd, sw.Wuk[k - 2], sw.bg[k - 1], sw.Wdk[k - 1],
+                                       sw.Wfk[k - 1], vdn, vdfn);
+#pragma unroll
+          for (int i = 0; i < 24; ++i) vd[i] = vdn[i];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) vdf[i] = vdfn[i];
+        }
+        write_extra_block(X, r, vd, vdf, f);
+        publish();
+        // ---- E(k)b: m_k = m_{k-1} + silu(S_k + b_k)
+        wait_d();
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          float v[32];
+          tmem_ld32(tl + TM_S + c0, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float m[8];
+            x_load8(X, r, c0 + q * 8, m);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = c0 + q * 8 + i;
+              m[i] += silu_fast(v[q * 8 + i] + sw.bk[k - 1][c]);
+              if (k == 3) adot = fmaf(m[i], sw.wa[c], adot);
+            }
+            x_store8(X, r, c0 + q * 8, m);
+          }
+        }
+        publish();
+      }
+      // ---- E4: gate_3 and the last m.v update
+      wait_d();
+      {
+        float dummy1[24], dummy2[9];
+        gate_update<8, false, true>(tl, TM_U1, vd, sw.Wuk[2], sw.bg[3], nullptr, nullptr, dummy1, dummy2);
+      }
+      const float attn = sigmoid_fast(adot + sw.ba[0]);
+      // ---- segmented sum over the source node (atomics where a row is cut by a 32-edge window)
+      named_bar_sync(1, TMT);     // sRow/sB/sNa of all rows visible
+      for (int chunk = 0; chunk < 11; ++chunk) {
+        float v[32];
+        if (chunk < 8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x_load8(X, r, chunk * 32 + q * 8, v + q * 8);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= attn;
+        } else {
+          tmem_ld32(tl + TM_MV + (chunk - 8) * 32, v);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) T.sT[r][i] = v[i];
+        named_bar_sync(1, TMT);
+        {
+          const int c = tid & 31, q0 = (tid >> 5) * 32;
+          float acc = 0.f;
+          int cur = -1;
+          bool first_ok = false;
+          for (int rr = q0; rr < q0 + 32; ++rr) {
+            const int rw = T.sRow[rr];
+            if (rw < 0) break;
+            if (rw != cur) { cur = rw; acc = 0.f; first_ok = (T.sB[rr] == 0); }
+            acc += T.sT[rr][c];
+            const bool last = (rr == q0 + 31) || (T.sRow[rr + 1] != rw);
+            if (last) {
+              float* dst = w.agg + (size_t)rw * kMsg + chunk * 32 + c;
+              if (first_ok && T.sB[rr] == T.sNa[rr] - 1) *dst = acc;
+              else atomicAdd(dst, acc);
+            }
+          }
+        }
+        named_bar_sync(1, TMT);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 512);
+}
+
+// ============================================================================================ launchers
+cudaError_t tc_configure() {
+  cudaError_t e = cudaFuncSetAttribute(k_edge_message_tc<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)TC_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_edge_message_tc<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              2 * X_BLOCK + 2 * RING_STAGE + 1024);
+}
+
+bool tc_supported(int Ed, int Xd) { return (Ed == 64 && Xd == 16) || (Ed == 16 && Xd == 8); }
+
+void launch_tc_pack(cudaStream_t st, const LayerW& lw, const Dims& d, unsigned char* blob) {
+  const long long rows = (long long)tc_nc0(d.Ed, d.Xd) * 256 + 3 * (4 * 320 + 256) + 4 * 32;
+  const long long total = rows * 64;
+  k_tc_pack_layer<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lw, d, blob);
+}
+
+void launch_edge_message_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const unsigned char* blob,
+                            const Work& w, int num_sms) {
+  const int ntiles = (int)((p.E + TMT - 1) / TMT);
+  if (ntiles == 0) return;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  if (d.Ed == 64) k_edge_message_tc<64, 16><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, lw, blob, w, ntiles);
+  else k_edge_message_tc<16, 8><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, lw, blob, w, ntiles);
+}
+
+void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C) {
+  k_selftest_pack<<<(320 * 128 + 255) / 256, 256, 0, st>>>(W, img_scratch);
+  k_umma_selftest<<<1, TC_THREADS, 2 * X_BLOCK + 2 * RING_STAGE + 1024, st>>>(A, img_scratch, C);
+}
+
+}  // namespace bdiff

@@ -47,4 +47,13 @@ void launch_edge_index(cudaStream_t st, const Plan& p, long long* out);
 void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
                  int kpad, int nout);
 
+// tensor-core edge pass (bdiff_edge_tc.cu)
+cudaError_t tc_configure();
+bool tc_supported(int Ed, int Xd);
+size_t tc_blob_bytes(int Ed, int Xd);
+void launch_tc_pack(cudaStream_t st, const LayerW& lw, const Dims& d, unsigned char* blob);
+void launch_edge_message_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const unsigned char* blob,
+                            const Work& w, int num_sms);
+void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
+
 }  // namespace bdiff

@@ -1,0 +1,135 @@
+// bdiff_tc.cuh — tcgen05 / TMEM / UMMA-descriptor helpers for the tensor-core edge pass (sm_100a).
+//
+// Conventions used by every UMMA operand in this library (bf16, K-major, 128-byte swizzle):
+//   an operand "K-block" is [rows][64 bf16] = rows x 128 B, 1024-byte aligned; element (r, k) lives at
+//       r*128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7)*2            (the TMA SWIZZLE_128B pattern)
+//   the shared-memory descriptor points at the block (plus 32 B per K=16 step, plus r0*128 for a row offset
+//   that is a multiple of 8), SBO = 1024 B (8 rows), LBO unused, version 1, layout SWIZZLE_128B.
+//   Accumulators: M=128 rows -> TMEM lanes 0..127, N columns -> consecutive 32-bit TMEM columns.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "bdiff_common.cuh"
+
+namespace bdiff {
+
+__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {   // byte offset inside a K-block
+  return (uint32_t)(r * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+// 64-bit UMMA shared-memory descriptor for a K-major SWIZZLE_128B operand at byte address `saddr`.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address  [0,14)
+  d |= (uint64_t)0 << 16;                          // leading byte offset [16,30): unused (one atom along K)
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;     // stride byte offset  [32,46): 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version  [46,48) = 1 on sm_100
+  d |= (uint64_t)2 << 61;                          // layout type [61,64): SWIZZLE_128B
+  return d;
+}
+
+// 32-bit instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N given.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n, bool negate_a) {
+  uint32_t d = 0;
+  d |= 1u << 4;                    // c_format = F32
+  d |= 1u << 7;                    // a_format = BF16
+  d |= 1u << 10;                   // b_format = BF16
+  d |= (negate_a ? 1u : 0u) << 13; // a_negate
+  d |= (uint32_t)(n >> 3) << 17;   // n_dim
+  d |= (uint32_t)(128 >> 4) << 24; // m_dim
+  return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          bool accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate ? 1u : 0u)
+      : "memory");
+}
+
+// All previously issued MMAs of this thread arrive (once) on `bar` when they complete.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // same warp that allocated
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// TMEM -> registers: this thread's lane (32*(warp%4) + laneid), `N` consecutive 32-bit columns from taddr.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// registers -> TMEM (per-thread scratch columns)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// fast activations for the tensor path (one MUFU each; operands are rounded to bf16 anyway)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(h);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace bdiff

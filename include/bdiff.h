@@ -78,6 +78,16 @@ BDIFF_API int32_t bdiff_set_weight(bdiff_handle* h, void* stream, const char* na
 /* Number of reference parameter tensors still missing (0 = ready); -errno on error. */
 BDIFF_API int32_t bdiff_weights_missing(const bdiff_handle* h);
 
+/* Finishes weight preparation once every parameter is set (tensor mode: builds the pre-swizzled bf16 weight
+ * K-blocks the TMA producer streams).  Called by the host after load_state_dict so that nothing but the forward
+ * kernels runs inside a captured CUDA graph.  Idempotent. */
+BDIFF_API int32_t bdiff_prepare(bdiff_handle* h, void* stream);
+
+/* Hardware self test of the tcgen05 machinery the tensor mode relies on (descriptors, 128B swizzle, TMA bulk
+ * copy, TMEM load/store): C[128,328] <- [A W^T (320 cols; the last 32 negated) | scratch round trip (8 cols)]
+ * for A fp32[128,128], W fp32[320,128] (device pointers, rounded to bf16 inside).  Synchronises. */
+BDIFF_API int32_t bdiff_selftest_umma(void* stream, const float* A, const float* W, float* C);
+
 /* Replaces: GCPNetDynamics.get_fully_connected_edge_index (gcpnet.py:1054-1066) — as an implicit plan.
  * batch_index int64[N] (sorted molecule ids, as every caller provides), mask uint8[N].  Builds the
  * per-molecule offsets the kernels enumerate edges from; *num_edges_host receives E = sum_k nact_k^2.

@@ -1,0 +1,80 @@
+"""GPU tests of the tensor-core (tcgen05) path.
+
+Tolerances (tensor mode = bf16 operands, fp32 accumulation in TMEM, tanh.approx activations): the hardware
+self test is compared with a bf16-rounded fp32 matmul at 1e-3 relative; a full denoiser forward is compared with
+the reference golden output at max-abs <= 2e-2 * max(1,|ref|) and rms <= 5e-3 * rms(ref)... (SURVEY.md §8c:
+emulated bf16/TF32 operand rounding of the reference itself gives max-abs 6e-3, rms 1.6e-3).
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+import gcpnet_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_umma_selftest_matches_bf16_matmul():
+    import bdiff
+    lib = bdiff.load_library()
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn((128, 128), generator=g).cuda()
+    w = torch.randn((320, 128), generator=g).cuda()
+    c = torch.zeros((128, 328), device="cuda")
+    rc = lib.bdiff_selftest_umma(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(a.data_ptr()),
+                                 C.c_void_p(w.data_ptr()), C.c_void_p(c.data_ptr()))
+    assert rc == 0
+    ref = a.bfloat16().float() @ w.bfloat16().float().t()
+    ref[:, 288:] = -ref[:, 288:]
+    err = (c[:, :320] - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-3, f"UMMA self test rel err {err:.3e}"
+    scratch = torch.arange(128 * 8, device="cuda", dtype=torch.float32).reshape(128, 8)
+    assert torch.equal(c[:, 320:], scratch)
+
+
+def make_net(cname, seed, mode, scale=1.0):
+    import bdiff
+    ocfg = O.config_named(cname)
+    sd = O.random_state_dict(ocfg, seed, scale=scale)
+    net = bdiff.GCPNetDynamicsB200(config=bdiff.DenoiserConfig.named(cname), mode=mode)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), ocfg, sd
+
+
+@pytest.mark.parametrize("name", ["qm9_small_masked", "qm9_tiny_sizes", "qm9_b4_n19", "qm9_cond", "geom_mixed",
+                                  "geom_max181"])
+def test_tensor_forward_close_to_reference(name):
+    fx = load_golden(name)
+    net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], "tensor")
+    ctx = fx["context"].cuda() if fx["context"] is not None else None
+    out = net.denoise(fx["batch_index"].cuda(), fx["mask"].cuda(), fx["xh"].cuda(), fx["t"].cuda(), ctx).cpu()
+    ref = fx["net_out"]
+    scale = max(1.0, ref.abs().max().item())
+    max_abs = (out - ref).abs().max().item()
+    rms = (out - ref).pow(2).mean().sqrt().item()
+    print(f"{name}: tensor-mode max|diff| {max_abs:.3e}, rms {rms:.3e} (|ref|max {ref.abs().max().item():.3g})")
+    assert torch.isfinite(out).all()
+    assert max_abs <= 2e-2 * scale and rms <= 5e-3 * scale
+
+
+def test_tensor_and_parity_modes_agree_full_size():
+    """QM9 B=128: tensor mode vs parity mode on the same input (both on the GPU)."""
+    g = torch.Generator().manual_seed(4)
+    b, nat = 128, 19
+    n = b * nat
+    bi = torch.repeat_interleave(torch.arange(b), torch.full((b,), nat)).cuda()
+    mask = torch.ones(n, dtype=torch.bool, device="cuda")
+    xh = torch.randn((n, 9), generator=g)
+    _, xc = O.centralize(xh[:, :3], bi.cpu(), mask.cpu(), b)
+    xh = torch.cat((xc, xh[:, 3:]), -1).cuda()
+    t = torch.full((n, 1), 0.5, device="cuda")
+    outs = {}
+    for mode in ("parity", "tensor"):
+        net, _, _ = make_net("qm9", 7, mode)
+        outs[mode] = net.denoise(bi, mask, xh, t)
+    d = (outs["tensor"] - outs["parity"])
+    scale = max(1.0, outs["parity"].abs().max().item())
+    print(f"full-size tensor vs parity: max {d.abs().max().item():.3e} rms {d.pow(2).mean().sqrt().item():.3e}")
+    assert d.abs().max().item() <= 2e-2 * scale and d.pow(2).mean().sqrt().item() <= 5e-3 * scale
