@@ -1,0 +1,58 @@
+"""CPU, world_size 2 over gloo: molecule sharding (LPT by n^2) + the single final gather restore the global
+order — the N>1 path of bench.py / bdiff.distributed without a GPU (the per-rank sampler is faked)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeSampler:
+    """Stands in for GCDMSampler: row j of molecule with n atoms is [n, j, 100 n + j]."""
+
+    def sample(self, num_nodes, context=None, num_timesteps=None):
+        rows = []
+        for n in num_nodes.tolist():
+            for j in range(n):
+                rows.append([float(n), float(j), float(100 * n + j)])
+        out = torch.tensor(rows).reshape(-1, 3)
+        return out, None, None
+
+
+def _worker(rank, world, port, sizes, results):
+    sys.path.insert(0, os.path.join(ROOT, "bio-diffusion_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bdiff.distributed import sample_sharded
+    out, mine = sample_sharded(FakeSampler(), torch.tensor(sizes))
+    results[rank] = (out, mine)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_lpt_shards_balance_and_cover():
+    sys.path.insert(0, os.path.join(ROOT, "bio-diffusion_b200"))
+    from bdiff.distributed import lpt_shards
+    sizes = [181, 3, 44, 44, 30, 61, 25, 19, 19, 100, 7, 90]
+    shards = lpt_shards(sizes, 4)
+    assert sorted(i for s in shards for i in s) == list(range(len(sizes)))
+    loads = [sum(sizes[i] ** 2 for i in s) for s in shards]
+    assert max(loads) <= 181 ** 2 + 1      # the biggest molecule bounds the best possible makespan here
+    assert lpt_shards(sizes, 1) == [list(range(len(sizes)))]
+    assert lpt_shards([19] * 8, 4) == [[0, 4], [1, 5], [2, 6], [3, 7]]
+
+
+def test_two_rank_gather_restores_global_order():
+    sizes = [5, 19, 3, 12, 7, 19, 2]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(2, 29517, sizes, results), nprocs=2, join=True)
+    expect, _, _ = FakeSampler().sample(torch.tensor(sizes))
+    for rank in (0, 1):
+        out, mine = results[rank]
+        assert torch.equal(out, expect)
+    assert sorted(results[0][1] + results[1][1]) == list(range(len(sizes)))
