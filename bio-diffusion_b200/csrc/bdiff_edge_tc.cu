@@ -11,7 +11,8 @@
 //     only A operand ever needed is m.s;
 //   * the equivariant vector channel (32x3 per edge) lives in TMEM scratch columns of the owning lane and is
 //     updated with thread-local FMAs (weights broadcast from shared memory);
-//   * warp roles: warps 0-3 epilogue/compute, warp 4 TMA producer (+TMEM allocator), warp 5 MMA issuer.
+//   * warp roles: warps 0-7 epilogue/compute (a thread PAIR per edge), warp 8 TMA producer (+TMEM allocator),
+//     warp 9 MMA issuer.
 #include "bdiff_kernels.h"
 #include "bdiff_tc.cuh"
 
@@ -179,6 +180,13 @@ __global__ void k_selftest_pack(const float* __restrict__ W, unsigned char* __re
 }
 
 // --------------------------------------------------------------------------------------------- fused kernel
+// Thread roles: warps 0-7 epilogue/compute — edge r of the tile is owned by the thread PAIR (r, r+128): "half" 0
+// works on accumulator columns [0,128) and vector channels [0,16), half 1 on columns [128,256) and channels
+// [16,32) (both warps of a pair address the same TMEM lanes: lane quarter = warp % 4); warp 8 = TMA producer
+// (+ TMEM allocator), warp 9 = MMA issuer.
+constexpr int TC_EPI = 256;
+constexpr int TC_THREADS2 = TC_EPI + 64;
+
 struct SmallW {            // fp32 copies of the thread-local (vector channel) weights, broadcast-read
   float Wd0x[16 * 20];     // [Xd][hid0]
   float Wf0x[16 * 3];      // [Xd][3]
@@ -193,8 +201,9 @@ struct SmallW {            // fp32 copies of the thread-local (vector channel) w
 };
 
 struct TcSmemTail {
-  float sT[TMT][33];       // transpose buffer of the final segmented reduction (32 columns at a time)
+  float sT[2][TMT][33];    // per-half transpose buffer of the final reduction; reused as the pair-exchange buffer
   SmallW sw;
+  float sAttn[2][TMT];
   int sRow[TMT], sCol[TMT], sB[TMT], sNa[TMT];
   uint64_t full[2], empty[2], a_ready, d_full;
   uint32_t tmem_ptr;
@@ -206,26 +215,28 @@ __device__ __forceinline__ void x_store8(unsigned char* X, int r, int kk, const 
   *reinterpret_cast<uint4*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63)) =
       make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
+__device__ __forceinline__ void x_store1(unsigned char* X, int r, int kk, float v) {
+  *reinterpret_cast<__nv_bfloat16*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63)) = __float2bfloat16_rn(v);
+}
 __device__ __forceinline__ void x_load8(const unsigned char* X, int r, int kk, float* v) {
   const uint4 u = *reinterpret_cast<const uint4*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63));
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y;
 }
 
-// Gate of the previous GCP from TMEM (U), vector-message update in TMEM scratch, and vector_down /
-// vector_down_frames of the NEXT GCP accumulated on the fly.  HP = hidden dim of the previous GCP.
+// Gate of the previous GCP from TMEM (U), vector-message update in TMEM scratch for this thread's 16 channels,
+// and this thread's partial vector_down / vector_down_frames sums of the NEXT GCP.
+// HP = hidden dim of the previous GCP; vdp = its vector_down output (full, [HP][3]).
 template <int HP, bool FIRST, bool LAST>
-__device__ __forceinline__ void gate_update(uint32_t tl, int ucol, const float* __restrict__ vdp,
+__device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, const float* __restrict__ vdp,
                                             const float* __restrict__ Wu, const float* __restrict__ bgp,
                                             const float* __restrict__ Wdn, const float* __restrict__ Wfn,
-                                            float* __restrict__ vdn, float* __restrict__ vdfn) {
+                                            float* __restrict__ part) {   // part[33]: partial VD_next(24)+VDF_next(9)
   if (!LAST) {
 #pragma unroll
-    for (int i = 0; i < 24; ++i) vdn[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) vdfn[i] = 0.f;
+    for (int i = 0; i < 33; ++i) part[i] = 0.f;
   }
-  for (int oc = 0; oc < 4; ++oc) {
+  for (int oc = half * 2; oc < half * 2 + 2; ++oc) {
     float u[8], mv[24];
     tmem_ld8(tl + ucol + oc * 8, u);
     if (!FIRST) {
@@ -255,50 +266,35 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int ucol, const float* 
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = oc * 8 + j;
+        const float4 wd0 = *reinterpret_cast<const float4*>(Wdn + c * 8), wd1 = *reinterpret_cast<const float4*>(Wdn + c * 8 + 4);
+        const float wd[8] = {wd0.x, wd0.y, wd0.z, wd0.w, wd1.x, wd1.y, wd1.z, wd1.w};
 #pragma unroll
         for (int h = 0; h < 8; ++h) {
-          const float wd = Wdn[c * 8 + h];
-          vdn[h * 3 + 0] = fmaf(wd, mv[j * 3 + 0], vdn[h * 3 + 0]);
-          vdn[h * 3 + 1] = fmaf(wd, mv[j * 3 + 1], vdn[h * 3 + 1]);
-          vdn[h * 3 + 2] = fmaf(wd, mv[j * 3 + 2], vdn[h * 3 + 2]);
+          part[h * 3 + 0] = fmaf(wd[h], mv[j * 3 + 0], part[h * 3 + 0]);
+          part[h * 3 + 1] = fmaf(wd[h], mv[j * 3 + 1], part[h * 3 + 1]);
+          part[h * 3 + 2] = fmaf(wd[h], mv[j * 3 + 2], part[h * 3 + 2]);
         }
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
           const float wf = Wfn[c * 3 + ch];
-          vdfn[ch * 3 + 0] = fmaf(wf, mv[j * 3 + 0], vdfn[ch * 3 + 0]);
-          vdfn[ch * 3 + 1] = fmaf(wf, mv[j * 3 + 1], vdfn[ch * 3 + 1]);
-          vdfn[ch * 3 + 2] = fmaf(wf, mv[j * 3 + 2], vdfn[ch * 3 + 2]);
+          part[24 + ch * 3 + 0] = fmaf(wf, mv[j * 3 + 0], part[24 + ch * 3 + 0]);
+          part[24 + ch * 3 + 1] = fmaf(wf, mv[j * 3 + 1], part[24 + ch * 3 + 1]);
+          part[24 + ch * 3 + 2] = fmaf(wf, mv[j * 3 + 2], part[24 + ch * 3 + 2]);
         }
       }
     }
   }
 }
 
-// [vn(8) | q(9) | 0...] of the next GCP -> A K-block 4, columns 0..31
-__device__ __forceinline__ void write_extra_block(unsigned char* X, int r, const float* vd, const float* vdf,
-                                                  const float* f) {
-  float a[32];
-#pragma unroll
-  for (int h = 0; h < 8; ++h) a[h] = safe_norm3(vd[h * 3], vd[h * 3 + 1], vd[h * 3 + 2]);
-#pragma unroll
-  for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax)
-      a[8 + ch * 3 + ax] = f[ax * 3] * vdf[ch * 3] + f[ax * 3 + 1] * vdf[ch * 3 + 1] + f[ax * 3 + 2] * vdf[ch * 3 + 2];
-#pragma unroll
-  for (int i = 17; i < 32; ++i) a[i] = 0.f;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) x_store8(X, r, 256 + q * 8, a + q * 8);
-}
-
 template <int ED, int XD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS2, 1)
     k_edge_message_tc(Plan p, LayerW lw, const unsigned char* __restrict__ blob, Work w, int ntiles) {
   constexpr int HID0 = (64 + XD) / 4;
+  constexpr int H2 = HID0 / 2;             // vector_down rows of GCP 0 computed per half
   constexpr int K0RAW = ED + HID0 + 9;
   constexpr int K0S = (K0RAW + 15) / 16;
   constexpr int NC0 = (K0S + 3) / 4;
-  static_assert(HID0 * 3 <= 64 && HID0 + 9 <= 32, "scratch layout");
+  static_assert(HID0 % 2 == 0 && H2 * 3 <= 32 && HID0 + 9 <= 32 && ED % 16 == 0, "layout");
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -310,24 +306,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (tid == 0) {
     mbar_init(&T.full[0], 1); mbar_init(&T.full[1], 1);
     mbar_init(&T.empty[0], 1); mbar_init(&T.empty[1], 1);
-    mbar_init(&T.a_ready, TMT);
+    mbar_init(&T.a_ready, TC_EPI);
     mbar_init(&T.d_full, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(&T.tmem_ptr, 512);
-  // small weights -> shared memory (all threads)
+  if (warp == 8) tmem_alloc(&T.tmem_ptr, 512);
   {
     SmallW& s = T.sw;
-    for (int i = tid; i < XD * HID0; i += TC_THREADS) s.Wd0x[i] = lw.Wd0x[i];
-    for (int i = tid; i < XD * 3; i += TC_THREADS) s.Wf0x[i] = lw.Wf0x[i];
-    for (int i = tid; i < HID0 * 32; i += TC_THREADS) s.Wu0[i] = lw.Wu0[i];
+    for (int i = tid; i < XD * HID0; i += TC_THREADS2) s.Wd0x[i] = lw.Wd0x[i];
+    for (int i = tid; i < XD * 3; i += TC_THREADS2) s.Wf0x[i] = lw.Wf0x[i];
+    for (int i = tid; i < HID0 * 32; i += TC_THREADS2) s.Wu0[i] = lw.Wu0[i];
     for (int k = 0; k < 3; ++k) {
-      for (int i = tid; i < 256; i += TC_THREADS) { s.Wdk[k][i] = lw.Wdk[k][i]; s.Wuk[k][i] = lw.Wuk[k][i]; s.bk[k][i] = lw.bk[k][i]; }
-      for (int i = tid; i < 96; i += TC_THREADS) s.Wfk[k][i] = lw.Wfk[k][i];
-      for (int i = tid; i < 32; i += TC_THREADS) s.bg[k + 1][i] = lw.bgk[k][i];
+      for (int i = tid; i < 256; i += TC_THREADS2) { s.Wdk[k][i] = lw.Wdk[k][i]; s.Wuk[k][i] = lw.Wuk[k][i]; s.bk[k][i] = lw.bk[k][i]; }
+      for (int i = tid; i < 96; i += TC_THREADS2) s.Wfk[k][i] = lw.Wfk[k][i];
+      for (int i = tid; i < 32; i += TC_THREADS2) s.bg[k + 1][i] = lw.bgk[k][i];
     }
-    for (int i = tid; i < 32; i += TC_THREADS) s.bg[0][i] = lw.bg0[i];
-    for (int i = tid; i < 256; i += TC_THREADS) s.wa[i] = lw.wa[i];
+    for (int i = tid; i < 32; i += TC_THREADS2) s.bg[0][i] = lw.bg0[i];
+    for (int i = tid; i < 256; i += TC_THREADS2) s.wa[i] = lw.wa[i];
     if (tid == 0) s.ba[0] = lw.ba[0];
   }
   tc_fence_before();
@@ -335,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = T.tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================================================================== TMA producer (one lane)
     if (lane == 0) {
       uint32_t ci = 0;
@@ -357,7 +352,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (int j = 0; j < 4; ++j) push(32 * 128);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ======================================================================= MMA issuer (one lane)
     if (lane == 0) {
       const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
@@ -424,10 +419,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // ============================================================ epilogue / compute warps (thread t <-> edge t)
-    const int r = tid;
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    // ====================================================== epilogue / compute warps (thread pair <-> edge r)
+    const int half = tid >> 7, r = tid & 127;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const SmallW& sw = T.sw;
+    float* exch_mine = &T.sT[half][r][0];
+    const float* exch_other = &T.sT[half ^ 1][r][0];
     uint32_t pd = 0;
     auto wait_d = [&]() { mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); };
     auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); };
@@ -444,20 +441,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         row = p.act_idx[a0 + a];
         col = p.act_idx[a0 + b];
       }
-      T.sRow[r] = row; T.sCol[r] = col; T.sB[r] = b; T.sNa[r] = na;
+      if (half == 0) { T.sRow[r] = row; T.sCol[r] = col; T.sB[r] = b; T.sNa[r] = na; }
       float f[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q) f[q] = w.frames[(size_t)g * 9 + q];
       const float* pi = w.PI + (size_t)(row < 0 ? 0 : row) * kPStride;
       const float* pj = w.PJ + (size_t)(col < 0 ? 0 : col) * kPStride;
-      // ---- T0: A operand of GCP 0 = [e | vn0 | q0]; VD0 kept in TMEM scratch for the vector_up of GCP 0
+
+      // ---- T0: A operand of GCP 0 = [e | vn0 | q0]; VD0 goes to TMEM scratch for the vector_up of GCP 0
       {
-        const float* er = w.e + (size_t)g * ED;
+        // this half's share of e (ED/2 columns)
+        const float* er = w.e + (size_t)g * ED + half * (ED / 2);
 #pragma unroll
-        for (int c8 = 0; c8 < ED; c8 += 8) {
+        for (int c8 = 0; c8 < ED / 2; c8 += 8) {
           const float4 a = *reinterpret_cast<const float4*>(er + c8), bq = *reinterpret_cast<const float4*>(er + c8 + 4);
           const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-          x_store8(X, r, c8, v);
+          x_store8(X, r, half * (ED / 2) + c8, v);
         }
         float xi[XD * 3];
         const float* xr = w.xi + (size_t)g * (XD * 3);
@@ -466,57 +465,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const float4 a = *reinterpret_cast<const float4*>(xr + c4);
           xi[c4] = a.x; xi[c4 + 1] = a.y; xi[c4 + 2] = a.z; xi[c4 + 3] = a.w;
         }
-        float vd0[64];
+        // vector_down rows [half*H2, half*H2 + H2) of GCP 0 (split form: endpoint parts gathered)
+        float vdh[32];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) vd0[i] = 0.f;
-        float vdf0[9];
+        for (int i = 0; i < 32; ++i) vdh[i] = 0.f;
         if (row >= 0) {
 #pragma unroll
-          for (int i = 0; i < HID0 * 3; ++i) vd0[i] = pi[kH + i] + pj[kH + i];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) vdf0[i] = pi[kH + HID0 * 3 + i] + pj[kH + HID0 * 3 + i];
-        } else {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) vdf0[i] = 0.f;
+          for (int i = 0; i < H2 * 3; ++i) vdh[i] = pi[kH + half * H2 * 3 + i] + pj[kH + half * H2 * 3 + i];
         }
 #pragma unroll
         for (int c = 0; c < XD; ++c) {
 #pragma unroll
-          for (int h = 0; h < HID0; ++h) {
-            const float wd = sw.Wd0x[c * HID0 + h];
-            vd0[h * 3 + 0] = fmaf(wd, xi[c * 3 + 0], vd0[h * 3 + 0]);
-            vd0[h * 3 + 1] = fmaf(wd, xi[c * 3 + 1], vd0[h * 3 + 1]);
-            vd0[h * 3 + 2] = fmaf(wd, xi[c * 3 + 2], vd0[h * 3 + 2]);
-          }
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch) {
-            const float wf = sw.Wf0x[c * 3 + ch];
-            vdf0[ch * 3 + 0] = fmaf(wf, xi[c * 3 + 0], vdf0[ch * 3 + 0]);
-            vdf0[ch * 3 + 1] = fmaf(wf, xi[c * 3 + 1], vdf0[ch * 3 + 1]);
-            vdf0[ch * 3 + 2] = fmaf(wf, xi[c * 3 + 2], vdf0[ch * 3 + 2]);
+          for (int h = 0; h < H2; ++h) {
+            const float wd = sw.Wd0x[c * HID0 + half * H2 + h];
+            vdh[h * 3 + 0] = fmaf(wd, xi[c * 3 + 0], vdh[h * 3 + 0]);
+            vdh[h * 3 + 1] = fmaf(wd, xi[c * 3 + 1], vdh[h * 3 + 1]);
+            vdh[h * 3 + 2] = fmaf(wd, xi[c * 3 + 2], vdh[h * 3 + 2]);
           }
         }
-        float a0v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a0v[i] = 0.f;
+        for (int h = 0; h < H2; ++h)
+          x_store1(X, r, ED + half * H2 + h, safe_norm3(vdh[h * 3], vdh[h * 3 + 1], vdh[h * 3 + 2]));
 #pragma unroll
-        for (int h = 0; h < HID0; ++h) a0v[h] = safe_norm3(vd0[h * 3], vd0[h * 3 + 1], vd0[h * 3 + 2]);
+        for (int q = 0; q < 4; ++q) tmem_st8(tl + TM_VD0 + half * 32 + q * 8, vdh + q * 8);
+        if (half == 0) {
+          // vector_down_frames of GCP 0 and its scalarisation q0 (9 values), plus the zero padding
+          float vdf0[9];
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
+          for (int i = 0; i < 9; ++i) vdf0[i] = row >= 0 ? pi[kH + HID0 * 3 + i] + pj[kH + HID0 * 3 + i] : 0.f;
 #pragma unroll
-          for (int ax = 0; ax < 3; ++ax)
-            a0v[HID0 + ch * 3 + ax] =
-                f[ax * 3] * vdf0[ch * 3] + f[ax * 3 + 1] * vdf0[ch * 3 + 1] + f[ax * 3 + 2] * vdf0[ch * 3 + 2];
+          for (int c = 0; c < XD; ++c)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) x_store8(X, r, ED + q * 8, a0v + q * 8);
+            for (int ch = 0; ch < 3; ++ch) {
+              const float wf = sw.Wf0x[c * 3 + ch];
+              vdf0[ch * 3 + 0] = fmaf(wf, xi[c * 3 + 0], vdf0[ch * 3 + 0]);
+              vdf0[ch * 3 + 1] = fmaf(wf, xi[c * 3 + 1], vdf0[ch * 3 + 1]);
+              vdf0[ch * 3 + 2] = fmaf(wf, xi[c * 3 + 2], vdf0[ch * 3 + 2]);
+            }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) tmem_st8(tl + TM_VD0 + q * 8, vd0 + q * 8);
+          for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax)
+              x_store1(X, r, ED + HID0 + ch * 3 + ax,
+                       f[ax * 3] * vdf0[ch * 3] + f[ax * 3 + 1] * vdf0[ch * 3 + 1] + f[ax * 3 + 2] * vdf0[ch * 3 + 2]);
+#pragma unroll
+          for (int i = HID0 + 9; i < 32; ++i) x_store1(X, r, ED + i, 0.f);
+        }
       }
       publish();
 
-      // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col])
+      // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col]), this half's 128 columns
       wait_d();
-      for (int c0 = 0; c0 < 256; c0 += 32) {
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float v[32];
         tmem_ld32(tl + TM_S + c0, v);
 #pragma unroll
@@ -539,54 +539,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       float vd[24], vdf[9];
       float adot = 0.f;
       for (int k = 1; k <= 3; ++k) {
-        // ---- E(k)a: gate_{k-1}, m.v update, vector_down of GCP k -> A block 4
+        // ---- E(k)a: gate_{k-1}, m.v update (this half's 16 channels), vector_down of GCP k -> A block 4
         wait_d();
+        float part[33];
         if (k == 1) {
-          float vd0[64];
+          float vd0[HID0 * 3];
+          {
+            float t0[32], t1[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) tmem_ld8(tl + TM_VD0 + q * 8, vd0 + q * 8);
-          gate_update<HID0, true, false>(tl, TM_U0, vd0, sw.Wu0, sw.bg[0], sw.Wdk[0], sw.Wfk[0], vd, vdf);
+            for (int q = 0; q < 4; ++q) { tmem_ld8(tl + TM_VD0 + q * 8, t0 + q * 8); tmem_ld8(tl + TM_VD0 + 32 + q * 8, t1 + q * 8); }
+#pragma unroll
+            for (int i = 0; i < H2 * 3; ++i) { vd0[i] = t0[i]; vd0[H2 * 3 + i] = t1[i]; }
+          }
+          gate_update<HID0, true, false>(tl, half, TM_U0, vd0, sw.Wu0, sw.bg[0], sw.Wdk[0], sw.Wfk[0], part);
         } else {
-          float vdn[24], vdfn[9];
-          gate_update<8, false, false>(tl, ((k - 1) & 1) ? TM_U1 : TM_U0, vd, sw.Wuk[k - 2], sw.bg[k - 1], sw.Wdk[k - 1],
-                                       sw.Wfk[k - 1], vdn, vdfn);
-#pragma unroll
-          for (int i = 0; i < 24; ++i) vd[i] = vdn[i];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) vdf[i] = vdfn[i];
+          gate_update<8, false, false>(tl, half, ((k - 1) & 1) ? TM_U1 : TM_U0, vd, sw.Wuk[k - 2], sw.bg[k - 1],
+                                       sw.Wdk[k - 1], sw.Wfk[k - 1], part);
         }
-        write_extra_block(X, r, vd, vdf, f);
+#pragma unroll
+        for (int i = 0; i < 33; ++i) exch_mine[i] = part[i];
+        named_bar_sync(3, TC_EPI);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) vd[i] = part[i] + exch_other[i];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) vdf[i] = part[24 + i] + exch_other[24 + i];
+        {
+          // [vn(8) | q(9) | 0...] -> A K-block 4; half 0 writes columns 0..15, half 1 columns 16..31
+          float a[16];
+          if (half == 0) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) a[h] = safe_norm3(vd[h * 3], vd[h * 3 + 1], vd[h * 3 + 2]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ch = i / 3, ax = i - ch * 3;
+              a[8 + i] = f[ax * 3] * vdf[ch * 3] + f[ax * 3 + 1] * vdf[ch * 3 + 1] + f[ax * 3 + 2] * vdf[ch * 3 + 2];
+            }
+          } else {
+            a[0] = f[6] * vdf[6] + f[7] * vdf[7] + f[8] * vdf[8];      // q[8]: ch 2, axis 2
+#pragma unroll
+            for (int i = 1; i < 16; ++i) a[i] = 0.f;
+          }
+          x_store8(X, r, 256 + half * 16, a);
+          x_store8(X, r, 256 + half * 16 + 8, a + 8);
+        }
+        named_bar_sync(3, TC_EPI);     // exchange buffer may be overwritten by the next phase
         publish();
-        // ---- E(k)b: m_k = m_{k-1} + silu(S_k + b_k)
+        // ---- E(k)b: m_k = m_{k-1} + silu(S_k + b_k), this half's 128 columns
         wait_d();
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
           float v[32];
           tmem_ld32(tl + TM_S + c0, v);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float m[8];
             x_load8(X, r, c0 + q * 8, m);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sw.bk[k - 1][c0 + q * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sw.bk[k - 1][c0 + q * 8 + 4]);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int c = c0 + q * 8 + i;
-              m[i] += silu_fast(v[q * 8 + i] + sw.bk[k - 1][c]);
-              if (k == 3) adot = fmaf(m[i], sw.wa[c], adot);
+            for (int i = 0; i < 8; ++i) m[i] += silu_fast(v[q * 8 + i] + bb[i]);
+            if (k == 3) {
+              const float4 w0 = *reinterpret_cast<const float4*>(&sw.wa[c0 + q * 8]);
+              const float4 w1 = *reinterpret_cast<const float4*>(&sw.wa[c0 + q * 8 + 4]);
+              adot = fmaf(m[0], w0.x, adot); adot = fmaf(m[1], w0.y, adot); adot = fmaf(m[2], w0.z, adot);
+              adot = fmaf(m[3], w0.w, adot); adot = fmaf(m[4], w1.x, adot); adot = fmaf(m[5], w1.y, adot);
+              adot = fmaf(m[6], w1.z, adot); adot = fmaf(m[7], w1.w, adot);
             }
             x_store8(X, r, c0 + q * 8, m);
           }
         }
+        if (k == 3) T.sAttn[half][r] = adot;
         publish();
       }
       // ---- E4: gate_3 and the last m.v update
       wait_d();
       {
-        float dummy1[24], dummy2[9];
-        gate_update<8, false, true>(tl, TM_U1, vd, sw.Wuk[2], sw.bg[3], nullptr, nullptr, dummy1, dummy2);
+        float dummy[33];
+        gate_update<8, false, true>(tl, half, TM_U1, vd, sw.Wuk[2], sw.bg[3], nullptr, nullptr, dummy);
       }
-      const float attn = sigmoid_fast(adot + sw.ba[0]);
-      // ---- segmented sum over the source node (atomics where a row is cut by a 32-edge window)
-      named_bar_sync(1, TMT);     // sRow/sB/sNa of all rows visible
-      for (int chunk = 0; chunk < 11; ++chunk) {
+      tc_fence_before();
+      named_bar_sync(3, TC_EPI);     // m.v of both halves in TMEM, sAttn/sRow/... visible
+      tc_fence_after();
+      const float attn = sigmoid_fast(T.sAttn[0][r] + T.sAttn[1][r] + sw.ba[0]);
+      // ---- segmented sum over the source node.  Chunks of 32 message columns: 0..7 = m.s, 8..10 = m.v.
+      // half 0 reduces chunks {0,1,2,3,8}, half 1 {4,5,6,7,9,10}; each half has its own transpose buffer.
+      const int nchunk = half == 0 ? 5 : 6;
+      for (int it = 0; it < nchunk; ++it) {
+        const int chunk = it < 4 ? half * 4 + it : (half == 0 ? 8 : 5 + it);
         float v[32];
         if (chunk < 8) {
 #pragma unroll
@@ -597,10 +636,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tmem_ld32(tl + TM_MV + (chunk - 8) * 32, v);
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) T.sT[r][i] = v[i];
-        named_bar_sync(1, TMT);
+        for (int i = 0; i < 32; ++i) T.sT[half][r][i] = v[i];
+        named_bar_sync(1 + half, TMT);
         {
-          const int c = tid & 31, q0 = (tid >> 5) * 32;
+          const int c = r & 31, q0 = (r >> 5) * 32;
           float acc = 0.f;
           int cur = -1;
           bool first_ok = false;
@@ -608,7 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             const int rw = T.sRow[rr];
             if (rw < 0) break;
             if (rw != cur) { cur = rw; acc = 0.f; first_ok = (T.sB[rr] == 0); }
-            acc += T.sT[rr][c];
+            acc += T.sT[half][rr][c];
             const bool last = (rr == q0 + 31) || (T.sRow[rr + 1] != rw);
             if (last) {
               float* dst = w.agg + (size_t)rw * kMsg + chunk * 32 + c;
@@ -617,13 +656,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             }
           }
         }
-        named_bar_sync(1, TMT);
+        named_bar_sync(1 + half, TMT);
       }
+      named_bar_sync(3, TC_EPI);       // sRow / exchange buffers free for the next tile
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
 // ============================================================================================ launchers
@@ -650,8 +690,8 @@ void launch_edge_message_tc(cudaStream_t st, const Plan& p, const Dims& d, const
   const int ntiles = (int)((p.E + TMT - 1) / TMT);
   if (ntiles == 0) return;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  if (d.Ed == 64) k_edge_message_tc<64, 16><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, lw, blob, w, ntiles);
-  else k_edge_message_tc<16, 8><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p, lw, blob, w, ntiles);
+  if (d.Ed == 64) k_edge_message_tc<64, 16><<<grid, TC_THREADS2, TC_SMEM_BYTES, st>>>(p, lw, blob, w, ntiles);
+  else k_edge_message_tc<16, 8><<<grid, TC_THREADS2, TC_SMEM_BYTES, st>>>(p, lw, blob, w, ntiles);
 }
 
 void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C) {
