@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_umma_selftest(const float* __
                                                                  const unsigned char* __restrict__ wimg,
                                                                  float* __restrict__ C) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space -> LDS/STS, not generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* X = smem;                          // 2 K-blocks of A
   unsigned char* Wb = smem + 2 * X_BLOCK;           // 2 K-blocks of W (320 rows each)
   uint64_t* bars = reinterpret_cast<uint64_t*>(Wb + 2 * RING_STAGE);
@@ -297,7 +298,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
   static_assert(HID0 % 2 == 0 && H2 * 3 <= 32 && HID0 + 9 <= 32 && ED % 16 == 0, "layout");
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space -> LDS/STS, not generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* X = smem;
   unsigned char* ring = smem + 5 * X_BLOCK;
   TcSmemTail& T = *reinterpret_cast<TcSmemTail*>(ring + 2 * RING_STAGE);
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
         size_t off = 0;
         auto push = [&](uint32_t bytes) {
           const uint32_t s = ci & 1;
-          mbar_wait(&T.empty[s], ((ci >> 1) & 1) ^ 1);
+          mbar_wait_backoff(&T.empty[s], ((ci >> 1) & 1) ^ 1);
           mbar_expect_tx(&T.full[s], bytes);
           bulk_g2s(ring + s * RING_STAGE, blob + off, bytes, &T.full[s]);
           off += bytes;
@@ -359,10 +361,10 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
                      i32n = umma_idesc_bf16(32, true);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0;
-      auto wait_a = [&]() { mbar_wait(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
+      auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
       auto wait_w = [&]() -> uint32_t {
         const uint32_t s = ci & 1;
-        mbar_wait(&T.full[s], (ci >> 1) & 1);
+        mbar_wait_backoff(&T.full[s], (ci >> 1) & 1);
         tc_fence_after();
         return raddr + s * RING_STAGE;
       };
@@ -623,6 +625,28 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
       const float attn = sigmoid_fast(T.sAttn[0][r] + T.sAttn[1][r] + sw.ba[0]);
       // ---- segmented sum over the source node.  Chunks of 32 message columns: 0..7 = m.s, 8..10 = m.v.
       // half 0 reduces chunks {0,1,2,3,8}, half 1 {4,5,6,7,9,10}; each half has its own transpose buffer.
+      // Reducer mapping: warp handles the 32 rows q0..q0+31, lane = column.  Segment structure of those rows
+      // as warp-uniform bit masks (bit i <-> row q0+i).
+      const int q0 = (r >> 5) * 32;
+      uint32_t m_valid, m_start, m_end, m_store;
+      {
+        const int rw = T.sRow[q0 + lane];
+        const int rp = lane > 0 ? T.sRow[q0 + lane - 1] : -2;
+        const int rn = lane < 31 ? T.sRow[q0 + lane + 1] : -2;
+        m_valid = __ballot_sync(0xffffffffu, rw >= 0);
+        m_start = __ballot_sync(0xffffffffu, rw != rp);
+        m_end = __ballot_sync(0xffffffffu, rw != rn);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, T.sB[q0 + lane] == 0);                     // row starts here
+        const uint32_t b1 = __ballot_sync(0xffffffffu, T.sB[q0 + lane] == T.sNa[q0 + lane] - 1);   // row ends here
+        // a segment may be STORED (not atomically added) iff it begins at its row's first edge and ends at its last
+        uint32_t ok = 0, cur_ok = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if ((m_start >> i) & 1u) cur_ok = (b0 >> i) & 1u;
+          if (((m_end >> i) & 1u) && cur_ok && ((b1 >> i) & 1u)) ok |= 1u << i;
+        }
+        m_store = ok;
+      }
       const int nchunk = half == 0 ? 5 : 6;
       for (int it = 0; it < nchunk; ++it) {
         const int chunk = it < 4 ? half * 4 + it : (half == 0 ? 8 : 5 + it);
@@ -639,19 +663,16 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
         for (int i = 0; i < 32; ++i) T.sT[half][r][i] = v[i];
         named_bar_sync(1 + half, TMT);
         {
-          const int c = r & 31, q0 = (r >> 5) * 32;
+          float col[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) col[i] = T.sT[half][q0 + i][lane];
           float acc = 0.f;
-          int cur = -1;
-          bool first_ok = false;
-          for (int rr = q0; rr < q0 + 32; ++rr) {
-            const int rw = T.sRow[rr];
-            if (rw < 0) break;
-            if (rw != cur) { cur = rw; acc = 0.f; first_ok = (T.sB[rr] == 0); }
-            acc += T.sT[half][rr][c];
-            const bool last = (rr == q0 + 31) || (T.sRow[rr + 1] != rw);
-            if (last) {
-              float* dst = w.agg + (size_t)rw * kMsg + chunk * 32 + c;
-              if (first_ok && T.sB[rr] == T.sNa[rr] - 1) *dst = acc;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            acc = ((m_start >> i) & 1u) ? col[i] : acc + col[i];
+            if (((m_end & m_valid) >> i) & 1u) {
+              float* dst = w.agg + (size_t)T.sRow[q0 + i] * kMsg + chunk * 32 + lane;
+              if ((m_store >> i) & 1u) *dst = acc;
               else atomicAdd(dst, acc);
             }
           }
