@@ -67,8 +67,8 @@ struct bdiff_handle {
   DevBuf tu_buf;       // uniform t scalar
 
   // tensor-core path state (bdiff_edge_tc.cu): per-layer pre-swizzled bf16 weight blobs
-  DevBuf tc_blob;
-  size_t tc_layer_bytes = 0;
+  DevBuf tc_blob, tc_node_blob;
+  size_t tc_layer_bytes = 0, tc_node_layer_bytes = 0;
   bool tc_dirty = true;
   int num_sms = 148;
 
@@ -319,8 +319,11 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
       return BDIFF_EINVAL;
     }
     e = tc_configure();
+    if (e == cudaSuccess) e = tc_node_configure();
     h->tc_layer_bytes = tc_blob_bytes(d.Ed, d.Xd);
+    h->tc_node_layer_bytes = tc_node_blob_bytes();
     if (e == cudaSuccess) e = h->tc_blob.ensure(h->tc_layer_bytes * d.L);
+    if (e == cudaSuccess) e = h->tc_node_blob.ensure(h->tc_node_layer_bytes * d.L);
   }
   if (e != cudaSuccess) {
     g_create_error = std::string("configure_kernels: ") + cudaGetErrorString(e);
@@ -335,7 +338,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
 void bdiff_destroy(bdiff_handle* h) {
   if (!h) return;
   if (h->wbuf) cudaFree(h->wbuf);
-  h->plan_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release();
+  h->plan_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
   delete h;
 }
 
@@ -367,7 +370,10 @@ static void tc_prepare(bdiff_handle* h, cudaStream_t st) {
   if (h->cfg.mode != BDIFF_MODE_TENSOR || !h->tc_dirty) return;
   for (int l = 0; l < h->d.L; ++l) {
     launch_tc_pack(st, h->layers[l], h->d, static_cast<unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes);
-    h->launches++;
+    const int last = (l == h->d.L - 1);
+    launch_tc_pack_node(st, h->layers[l], h->layers[last ? l : l + 1], h->embed, h->d, last,
+                        static_cast<unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes);
+    h->launches += 2;
   }
   h->tc_dirty = false;
 }
@@ -460,7 +466,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   p.node_mol = reinterpret_cast<int*>(base + o_nm);
   p.edge_off = reinterpret_cast<long long*>(base + o_eo);
   p.mask = base + o_mk;
-  h->Npad = round_up(N, 16);
+  h->Npad = round_up(N, 128);
   h->Epad = (E + 127) / 128 * 128 + 128;
   e = ensure_work(h);
   if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "workspace: %s", cudaGetErrorString(e));
@@ -515,7 +521,12 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
       launch_edge_message(st, p, d, h->layers[l], w);
     mark();
     const bool last = (l == d.L - 1);
-    launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);
+    if (tensor)
+      launch_node_update_tc(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed,
+                            static_cast<const unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes, w,
+                            last ? 1 : 0, h->num_sms);
+    else
+      launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);
     mark();
     h->launches += 2;
   }

@@ -20,7 +20,6 @@ namespace bdiff {
 
 constexpr int TC_THREADS = 192;
 constexpr int TMT = 128;                 // edges per tile
-constexpr int X_BLOCK = TMT * 128;       // bytes of one A K-block (64 bf16 per row)
 constexpr int RING_STAGE = 320 * 128;    // bytes of the largest weight chunk (320 rows x 64 bf16)
 // TMEM column map (512 columns allocated)
 constexpr int TM_S = 0, TM_U0 = 256, TM_U1 = 288, TM_MV = 320, TM_VD0 = 416;
@@ -211,19 +210,6 @@ struct TcSmemTail {
 };
 
 constexpr size_t TC_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)RING_STAGE + sizeof(TcSmemTail) + 1024;
-
-__device__ __forceinline__ void x_store8(unsigned char* X, int r, int kk, const float* v) {   // kk % 8 == 0
-  *reinterpret_cast<uint4*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63)) =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
-__device__ __forceinline__ void x_store1(unsigned char* X, int r, int kk, float v) {
-  *reinterpret_cast<__nv_bfloat16*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63)) = __float2bfloat16_rn(v);
-}
-__device__ __forceinline__ void x_load8(const unsigned char* X, int r, int kk, float* v) {
-  const uint4 u = *reinterpret_cast<const uint4*>(X + (kk >> 6) * X_BLOCK + sw128_offset(r, kk & 63));
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = e.x; v[7] = e.y;
-}
 
 // Gate of the previous GCP from TMEM (U), vector-message update in TMEM scratch for this thread's 16 channels,
 // and this thread's partial vector_down / vector_down_frames sums of the NEXT GCP.

@@ -54,6 +54,13 @@ size_t tc_blob_bytes(int Ed, int Xd);
 void launch_tc_pack(cudaStream_t st, const LayerW& lw, const Dims& d, unsigned char* blob);
 void launch_edge_message_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const unsigned char* blob,
                             const Work& w, int num_sms);
+// tensor-core node pass (bdiff_node_tc.cu)
+cudaError_t tc_node_configure();
+size_t tc_node_blob_bytes();
+void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
+                         unsigned char* blob);
+void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
+                           const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
 void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
 
 }  // namespace bdiff
