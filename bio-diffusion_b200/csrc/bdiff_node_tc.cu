@@ -5,8 +5,9 @@
 // final scalar projection.  Tile = 128 nodes = the 128 TMEM lanes, a thread PAIR per node (half 0: accumulator
 // columns [0,128) / vector channels [0,16); half 1 the rest).  The A operand (bf16, K-major, 128B swizzle, 5
 // K-blocks) is rewritten in place between the chained GEMMs; weights stream from L2 as pre-swizzled bf16
-// K-blocks through a 2-stage TMA-bulk ring; the feed-forward vector gate  sigmoid(Wg Z2 + b)  is folded into the
-// neighbouring GEMMs via  Wg Z2 = Wg h_new - Wg h_old  (A-negate), like in the edge kernel.
+// K-blocks through a 3-stage TMA-bulk ring; the feed-forward vector gate  sigmoid(Wg Z2 + b)  gets its own small
+// N=32 MMA on the bf16 image of Z2 (folding it as Wg h_new - Wg h_old like in the edge kernel cancels badly here
+// because |h| >> |Z2| on the residual stream).
 // TMEM columns: S 0..255 | U 256..287 | chi (96) 288..383 | VD_ff (48) 384..431 | pair exchange 2x40 432..511.
 #include "bdiff_kernels.h"
 #include "bdiff_tc.cuh"
@@ -16,17 +17,18 @@ namespace bdiff {
 constexpr int NT_EPI = 256;
 constexpr int NT_THREADS = NT_EPI + 64;
 constexpr int NTM = 128;
-constexpr int NRING = 288 * 128;
+constexpr int NRING = 256 * 128;
+constexpr int NSTAGES = 3;
 constexpr int NM_S = 0, NM_U = 256, NM_CHI = 288, NM_VDF = 384, NM_EX = 432;
 
-size_t tc_node_blob_bytes() { return (size_t)(4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + 8 * 256) * 128; }
+size_t tc_node_blob_bytes() { return (size_t)(4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + 8 * 256) * 128; }
 
 // Per-layer bf16 blob in streaming order:
-//   G1a 4x[256]: W1[:, 0:256]   | G1b 4x[288]: W1[:, 256:512] + Wg_ff | G1c [256]: W1[:, 512:544]
-//   G2  4x[256]: W2             | G3a 4x[288]: Wp[:, 0:256] + Wg_ff   | G3b [256]: Wp[:, 256:288]
+//   G1a 4x[256]: W1[:, 0:256]   | G1b 4x[256]: W1[:, 256:512]        | G1c [256]: W1[:, 512:544]
+//   G2  4x[256]: W2             | Gg 4x[32]: Wg_ff                    | G3a 4x[256]: Wp[:, 0:256] | G3b [256]: Wp[:, 256:288]
 //   not last: G4 4x[256]: next.Wsi, G5 4x[256]: next.Wsj            last: Gp 5x[32]: projection scalar_out
 __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last, unsigned char* __restrict__ blob) {
-  const long long total_rows = 4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + (last ? 5 * 32 : 8 * 256);
+  const long long total_rows = 4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + (last ? 5 * 32 : 8 * 256);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_rows * 64) return;
   long long rowg = idx / 64;
@@ -43,10 +45,9 @@ __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last
   if (seg(4 * 256)) {
     const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
     v = lw.W1[(size_t)(j * 64 + kc) * 256 + r];
-  } else if (seg(4 * 288)) {
-    const int j = (int)(rowg / 288); r = (int)(rowg % 288); base += (size_t)j * 288 * 128;
-    const int kk = j * 64 + kc;
-    v = r < 256 ? lw.W1[(size_t)(256 + kk) * 256 + r] : lw.Wgf[(size_t)kk * 32 + (r - 256)];
+  } else if (seg(4 * 256)) {
+    const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
+    v = lw.W1[(size_t)(256 + j * 64 + kc) * 256 + r];
   } else if (seg(256)) {
     r = (int)rowg;
     const int kk = 512 + kc;
@@ -54,10 +55,12 @@ __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last
   } else if (seg(4 * 256)) {
     const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
     v = lw.W2[(size_t)(j * 64 + kc) * 256 + r];
-  } else if (seg(4 * 288)) {
-    const int j = (int)(rowg / 288); r = (int)(rowg % 288); base += (size_t)j * 288 * 128;
-    const int kk = j * 64 + kc;
-    v = r < 256 ? lw.Wp[(size_t)kk * 256 + r] : lw.Wgf[(size_t)kk * 32 + (r - 256)];
+  } else if (seg(4 * 32)) {
+    const int j = (int)(rowg / 32); r = (int)(rowg % 32); base += (size_t)j * 32 * 128;
+    v = lw.Wgf[(size_t)(j * 64 + kc) * 32 + r];
+  } else if (seg(4 * 256)) {
+    const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
+    v = lw.Wp[(size_t)(j * 64 + kc) * 256 + r];
   } else if (seg(256)) {
     r = (int)rowg;
     const int kk = 256 + kc;
@@ -88,11 +91,11 @@ struct SmallWN {
 struct NodeTcTail {
   SmallWN sw;
   float sDot[2][NTM];
-  uint64_t full[2], empty[2], a_ready, d_full;
+  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full;
   uint32_t tmem_ptr;
 };
 
-constexpr size_t NT_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)NRING + sizeof(NodeTcTail) + 1024;
+constexpr size_t NT_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING + sizeof(NodeTcTail) + 1024;
 
 __global__ void __launch_bounds__(NT_THREADS, 1)
     k_node_update_tc(Plan p, Dims d, LayerW lw, LayerW wn, EmbedW ew, const unsigned char* __restrict__ blob, Work w,
@@ -101,13 +104,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* X = smem;
   unsigned char* ring = smem + 5 * X_BLOCK;
-  NodeTcTail& T = *reinterpret_cast<NodeTcTail*>(ring + 2 * NRING);
+  NodeTcTail& T = *reinterpret_cast<NodeTcTail*>(ring + NSTAGES * NRING);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hid0 = d.hid0;
 
   if (tid == 0) {
-    mbar_init(&T.full[0], 1); mbar_init(&T.full[1], 1);
-    mbar_init(&T.empty[0], 1); mbar_init(&T.empty[1], 1);
+    for (int i = 0; i < NSTAGES; ++i) { mbar_init(&T.full[i], 1); mbar_init(&T.empty[i], 1); }
     mbar_init(&T.a_ready, NT_EPI);
     mbar_init(&T.d_full, 1);
     mbar_fence_init();
@@ -139,19 +141,17 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         size_t off = 0;
         auto push = [&](uint32_t bytes) {
-          const uint32_t s = ci & 1;
-          mbar_wait_backoff(&T.empty[s], ((ci >> 1) & 1) ^ 1);
+          const uint32_t s = ci % NSTAGES;
+          mbar_wait_backoff(&T.empty[s], ((ci / NSTAGES) & 1) ^ 1);
           mbar_expect_tx(&T.full[s], bytes);
           bulk_g2s(ring + s * NRING, blob + off, bytes, &T.full[s]);
           off += bytes;
           ++ci;
         };
-        for (int j = 0; j < 4; ++j) push(256 * 128);
-        for (int j = 0; j < 4; ++j) push(288 * 128);
-        push(256 * 128);
-        for (int j = 0; j < 4; ++j) push(256 * 128);
-        for (int j = 0; j < 4; ++j) push(288 * 128);
-        push(256 * 128);
+        for (int j = 0; j < 9; ++j) push(256 * 128);      // G1a, G1b, G1c
+        for (int j = 0; j < 4; ++j) push(256 * 128);      // G2
+        for (int j = 0; j < 4; ++j) push(32 * 128);       // Gg
+        for (int j = 0; j < 5; ++j) push(256 * 128);      // G3a, G3b
         if (!last) { for (int j = 0; j < 8; ++j) push(256 * 128); }
         else { for (int j = 0; j < 5; ++j) push(32 * 128); }
       }
@@ -159,18 +159,17 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
   } else if (warp == 9) {
     // ======================================================================= MMA issuer (one lane)
     if (lane == 0) {
-      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
-                     i32n = umma_idesc_bf16(32, true);
+      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0;
       auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
       auto wait_w = [&]() -> uint32_t {
-        const uint32_t s = ci & 1;
-        mbar_wait_backoff(&T.full[s], (ci >> 1) & 1);
+        const uint32_t s = ci % NSTAGES;
+        mbar_wait_backoff(&T.full[s], (ci / NSTAGES) & 1);
         tc_fence_after();
         return raddr + s * NRING;
       };
-      auto done_w = [&]() { umma_commit(&T.empty[ci & 1]); ++ci; };
+      auto done_w = [&]() { umma_commit(&T.empty[ci % NSTAGES]); ++ci; };
       auto gemm256 = [&](bool fresh) {     // 4 K-blocks of X against 4 chunks of 256 rows -> S
         for (int j = 0; j < 4; ++j) {
           const uint32_t wb = wait_w();
@@ -180,15 +179,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
           done_w();
         }
       };
-      auto gemm288 = [&](bool fresh_s, bool negate_u, bool fresh_u) {   // ... plus 32 gate columns -> U
+      auto gemm_gate = [&]() {             // U = Z2 . Wg^T (N=32), 4 chunks of 32 rows
         for (int j = 0; j < 4; ++j) {
           const uint32_t wb = wait_w();
-          for (int s = 0; s < 4; ++s) {
-            const uint64_t ad = umma_desc_sw128(xaddr + j * X_BLOCK + s * 32);
-            umma_bf16(tmem + NM_S, ad, umma_desc_sw128(wb + s * 32), i256, fresh_s ? (j | s) > 0 : true);
-            umma_bf16(tmem + NM_U, ad, umma_desc_sw128(wb + 256 * 128 + s * 32), negate_u ? i32n : i32,
-                      fresh_u ? (j | s) > 0 : true);
-          }
+          for (int s = 0; s < 4; ++s)
+            umma_bf16(tmem + NM_U, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i32,
+                      (j | s) > 0);
           done_w();
         }
       };
@@ -200,9 +196,10 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G1a: agg_s . W1a
-        wait_a(); gemm288(false, true, true); gemm_extra(); umma_commit(&T.d_full); // G1b/c: + h . W1b, U = -Wg h, + [vn|q] . W1c
+        wait_a(); gemm256(false); gemm_extra(); umma_commit(&T.d_full);             // G1b/c: + h . W1b + [vn|q] . W1c
         wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G2: Y . W2
-        wait_a(); gemm288(true, false, false); umma_commit(&T.d_full);              // G3a: h_new . Wp, U += Wg h_new
+        wait_a(); gemm_gate(); umma_commit(&T.d_full);                              // Gg: U = Z2 . Wg
+        wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G3a: h_new . Wp
         wait_a(); gemm_extra(); umma_commit(&T.d_full);                             // G3b
         if (!last) {
           wait_a(); gemm256(true); umma_commit(&T.d_full);                          // G4: h_new . Wsi(next)
@@ -335,7 +332,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
       }
       publish();
-      // ---- E2: h_new = (h + S + b2) * mask  -> global h (fp32) and A blocks 0..3
+      // ---- E2a: Z2 = S + b2 -> A blocks 0..3 (bf16) for the gate MMA; h_new = (h + Z2) * mask -> global h (fp32)
       wait_d();
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float v[32];
@@ -344,16 +341,21 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         for (int q = 0; q < 8; ++q) {
           const float4 bb = *reinterpret_cast<const float4*>(&sw.b2[c0 + q * 4]);
           const float4 ho = *reinterpret_cast<const float4*>(hrow + c0 + q * 4);
-          float4 hn;
-          hn.x = (ho.x + v[q * 4 + 0] + bb.x) * m;
-          hn.y = (ho.y + v[q * 4 + 1] + bb.y) * m;
-          hn.z = (ho.z + v[q * 4 + 2] + bb.z) * m;
-          hn.w = (ho.w + v[q * 4 + 3] + bb.w) * m;
-          *reinterpret_cast<float4*>(hrow + c0 + q * 4) = hn;
-          v[q * 4 + 0] = hn.x; v[q * 4 + 1] = hn.y; v[q * 4 + 2] = hn.z; v[q * 4 + 3] = hn.w;
+          v[q * 4 + 0] += bb.x; v[q * 4 + 1] += bb.y; v[q * 4 + 2] += bb.z; v[q * 4 + 3] += bb.w;
+          *reinterpret_cast<float4*>(hrow + c0 + q * 4) = make_float4((ho.x + v[q * 4 + 0]) * m, (ho.y + v[q * 4 + 1]) * m,
+                                                                      (ho.z + v[q * 4 + 2]) * m, (ho.w + v[q * 4 + 3]) * m);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
+      }
+      publish();
+      // ---- E2b: after the gate MMA has consumed Z2, stage h_new (re-read in fp32) as the next A operand
+      wait_d();
+      for (int c0 = 0; c0 < 128; c0 += 8) {
+        const float4 a = *reinterpret_cast<const float4*>(hrow + half * 128 + c0);
+        const float4 b = *reinterpret_cast<const float4*>(hrow + half * 128 + c0 + 4);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        x_store8(X, r, half * 128 + c0, v);
       }
       publish();
       // ---- E3a: FF vector gate, chi_new for this half's 16 channels, vector_down of the position GCP
@@ -591,7 +593,7 @@ cudaError_t tc_node_configure() {
 
 void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
                          unsigned char* blob) {
-  const long long rows = 4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + (last ? 5 * 32 : 8 * 256);
+  const long long rows = 4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + (last ? 5 * 32 : 8 * 256);
   const long long total = rows * 64;
   k_tc_pack_node<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lw, wn, ew, d, last, blob);
 }
