@@ -5,7 +5,7 @@
 // final scalar projection.  Tile = 128 nodes = the 128 TMEM lanes, a thread PAIR per node (half 0: accumulator
 // columns [0,128) / vector channels [0,16); half 1 the rest).  The A operand (bf16, K-major, 128B swizzle, 5
 // K-blocks) is rewritten in place between the chained GEMMs; weights stream from L2 as pre-swizzled bf16
-// K-blocks through a 3-stage TMA-bulk ring; the feed-forward vector gate  sigmoid(Wg Z2 + b)  gets its own small
+// K-blocks through a 2-stage TMA-bulk ring; the feed-forward vector gate  sigmoid(Wg Z2 + b)  gets its own small
 // N=32 MMA on the bf16 image of Z2 (folding it as Wg h_new - Wg h_old like in the edge kernel cancels badly here
 // because |h| >> |Z2| on the residual stream).
 // TMEM columns: S 0..255 | U 256..287 | chi (96) 288..383 | VD_ff (48) 384..431 | pair exchange 2x40 432..511.
@@ -18,7 +18,7 @@ constexpr int NT_EPI = 256;
 constexpr int NT_THREADS = NT_EPI + 64;
 constexpr int NTM = 128;
 constexpr int NRING = 256 * 128;
-constexpr int NSTAGES = 3;
+constexpr int NSTAGES = 2;
 constexpr int NM_S = 0, NM_U = 256, NM_CHI = 288, NM_VDF = 384, NM_EX = 432;
 
 size_t tc_node_blob_bytes() { return (size_t)(4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + 8 * 256) * 128; }
@@ -90,12 +90,27 @@ struct SmallWN {
 
 struct NodeTcTail {
   SmallWN sw;
+  float sTw[8][32][33];    // per-warp 32x32 transposition scratch (coalesced global stores of accumulator tiles)
+  float sMask[NTM];
   float sDot[2][NTM];
   uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full;
   uint32_t tmem_ptr;
 };
 
 constexpr size_t NT_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING + sizeof(NodeTcTail) + 1024;
+
+// Coalesced staging of a [128 x 128] fp32 block (row stride ld floats) into A columns [kk0, kk0+128) as bf16:
+// each warp-iteration reads one contiguous 512-byte half-row and scatters 8-byte packs into the swizzled tile.
+__device__ __forceinline__ void stage_rows(unsigned char* X, const float* __restrict__ base, int ld, int kk0, int wih,
+                                           int lane) {
+  const int kk = kk0 + lane * 4;
+#pragma unroll 4
+  for (int rr = wih; rr < NTM; rr += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)rr * ld + lane * 4);
+    *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(rr, kk & 63)) =
+        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
 
 __global__ void __launch_bounds__(NT_THREADS, 1)
     k_node_update_tc(Plan p, Dims d, LayerW lw, LayerW wn, EmbedW ew, const unsigned char* __restrict__ blob, Work w,
@@ -230,8 +245,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       const int node = tile * NTM + r;
       const bool valid = node < p.N;
       const float m = (valid && p.mask[node]) ? 1.f : 0.f;
+      const int wih = warp & 3;                      // warp index inside the half == TMEM lane quarter
+      float (*tw)[33] = T.sTw[warp];
+      const int row0 = wih * 32;                     // first tile row of this warp
+      if (half == 0) T.sMask[r] = m;
       float* ag = w.agg + (size_t)node * kMsg;
-      float* hrow = w.h + (size_t)node * kH;
       float* crow = w.chi + (size_t)node * 96;
       float f[9];
       {
@@ -240,13 +258,8 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
         f[8] = w.fbar[(size_t)node * 12 + 8];
       }
-      // ---- T0: agg_s -> A blocks 0..3; vector_down (this half's 8 rows) / vector_down_frames of the FF GCP
-      for (int c0 = 0; c0 < 128; c0 += 8) {
-        const float4 a = *reinterpret_cast<const float4*>(ag + half * 128 + c0);
-        const float4 b = *reinterpret_cast<const float4*>(ag + half * 128 + c0 + 4);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        x_store8(X, r, half * 128 + c0, v);
-      }
+      // ---- T0: agg_s -> A blocks 0..3 (coalesced); vector_down (this half's 8 rows) / vector_down_frames of the FF GCP
+      stage_rows(X, w.agg + (size_t)tile * NTM * kMsg + half * 128, kMsg, half * 128, wih, lane);
       {
         float vdh[24], vdf[9];
 #pragma unroll
@@ -308,12 +321,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       publish();
       // ---- T0b: h -> A blocks 0..3 (after G1a has consumed agg_s)
       wait_d();
-      for (int c0 = 0; c0 < 128; c0 += 8) {
-        const float4 a = *reinterpret_cast<const float4*>(hrow + half * 128 + c0);
-        const float4 b = *reinterpret_cast<const float4*>(hrow + half * 128 + c0 + 4);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        x_store8(X, r, half * 128 + c0, v);
-      }
+      stage_rows(X, w.h + (size_t)tile * NTM * kH + half * 128, kH, half * 128, wih, lane);
       publish();
       // ---- E1: Y = silu(S + b1)
       wait_d();
@@ -332,7 +340,8 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
       }
       publish();
-      // ---- E2a: Z2 = S + b2 -> A blocks 0..3 (bf16) for the gate MMA; h_new = (h + Z2) * mask -> global h (fp32)
+      // ---- E2a: Z2 = S + b2 -> A blocks 0..3 (bf16) for the gate MMA; h_new = (h + Z2) * mask -> global h (fp32),
+      //      written through a per-warp 32x32 transpose so that every global access is a full 128-byte line
       wait_d();
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float v[32];
@@ -340,23 +349,22 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bb = *reinterpret_cast<const float4*>(&sw.b2[c0 + q * 4]);
-          const float4 ho = *reinterpret_cast<const float4*>(hrow + c0 + q * 4);
           v[q * 4 + 0] += bb.x; v[q * 4 + 1] += bb.y; v[q * 4 + 2] += bb.z; v[q * 4 + 3] += bb.w;
-          *reinterpret_cast<float4*>(hrow + c0 + q * 4) = make_float4((ho.x + v[q * 4 + 0]) * m, (ho.y + v[q * 4 + 1]) * m,
-                                                                      (ho.z + v[q * 4 + 2]) * m, (ho.w + v[q * 4 + 3]) * m);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
+        __syncwarp();
+        float* hb = w.h + ((size_t)tile * NTM + row0) * kH + c0 + lane;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) hb[(size_t)i * kH] = (hb[(size_t)i * kH] + tw[i][lane]) * T.sMask[row0 + i];
+        __syncwarp();
       }
       publish();
       // ---- E2b: after the gate MMA has consumed Z2, stage h_new (re-read in fp32) as the next A operand
       wait_d();
-      for (int c0 = 0; c0 < 128; c0 += 8) {
-        const float4 a = *reinterpret_cast<const float4*>(hrow + half * 128 + c0);
-        const float4 b = *reinterpret_cast<const float4*>(hrow + half * 128 + c0 + 4);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        x_store8(X, r, half * 128 + c0, v);
-      }
+      stage_rows(X, w.h + (size_t)tile * NTM * kH + half * 128, kH, half * 128, wih, lane);
       publish();
       // ---- E3a: FF vector gate, chi_new for this half's 16 channels, vector_down of the position GCP
       wait_d();
@@ -511,16 +519,17 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       if (!last) {
         // ---- E4: PI scalar part = S + b0 (this half's columns); vector parts of PI (half 0) / PJ (half 1)
         wait_d();
-        float* prow = w.PI + (size_t)node * kPStride;
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
           float v[32];
           tmem_ld32(tl + NM_S + c0, v);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(&sw.b0[c0 + q * 4]);
-            *reinterpret_cast<float4*>(prow + c0 + q * 4) =
-                make_float4(v[q * 4] + bb.x, v[q * 4 + 1] + bb.y, v[q * 4 + 2] + bb.z, v[q * 4 + 3] + bb.w);
-          }
+          for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
+          __syncwarp();
+          float* pb = w.PI + ((size_t)tile * NTM + row0) * kPStride + c0 + lane;
+          const float b0v = sw.b0[c0 + lane];
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) pb[(size_t)i * kPStride] = tw[i][lane] + b0v;
+          __syncwarp();
         }
         publish();
         {
@@ -555,13 +564,16 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         }
         // ---- E5: PJ scalar part = S
         wait_d();
-        float* jrow = w.PJ + (size_t)node * kPStride;
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
           float v[32];
           tmem_ld32(tl + NM_S + c0, v);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(jrow + c0 + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
+          __syncwarp();
+          float* pb = w.PJ + ((size_t)tile * NTM + row0) * kPStride + c0 + lane;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) pb[(size_t)i * kPStride] = tw[i][lane];
+          __syncwarp();
         }
       } else {
         // ---- Ep: projected scalars = U + bias
@@ -574,9 +586,13 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
             if (i < d.Hin) w.hproj[(size_t)node * 32 + i] = v[i] + sw.pbs[i];
         }
       }
-      // reset this node's aggregate row for the next layer's edge pass (its atomics need zeros)
-      for (int c0 = 0; c0 < 128; c0 += 4) *reinterpret_cast<float4*>(ag + half * 128 + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c0 = 0; c0 < 48; c0 += 4) *reinterpret_cast<float4*>(ag + kH + half * 48 + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      // reset the tile's aggregate rows for the next layer's edge pass (its atomics need zeros); the vector part was
+      // read by both halves in T0, so order the reset after everybody's reads
+      named_bar_sync(3, NT_EPI);
+      for (int rr = warp; rr < NTM; rr += 8) {
+        float4* z = reinterpret_cast<float4*>(w.agg + ((size_t)tile * NTM + rr) * kMsg);
+        for (int c4 = lane; c4 < kMsg / 4; c4 += 32) z[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       tc_fence_before();
       named_bar_sync(3, NT_EPI);     // both halves are done with S / U / scratch before the next tile's MMAs
       tc_fence_after();
