@@ -237,6 +237,107 @@ __global__ void __launch_bounds__(kThreads) k_edge_embed(Plan p, Dims d, EmbedW 
   }
 }
 
+// Thread-per-edge variant for the shipped dims (everything in registers, weights broadcast from shared memory).
+// Uses  vector_up(vector_down(xi))[o][x] = (sum_h Wu[h][o] wd[h]) * xi[x]  (the input has a single vector channel).
+template <int ED, int XD>
+__global__ void __launch_bounds__(128) k_edge_embed_tpe(Plan p, EmbedW ew, Work w) {
+  constexpr int KE = 1 + XD + 9;
+  __shared__ float sWs[KE * ED], sbs[ED], swd[XD], swf[4], sWg[ED * XD], sbg[XD], sUd[XD];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < KE * ED; i += 128) sWs[i] = ew.eWs[i];
+  for (int i = tid; i < ED; i += 128) sbs[i] = ew.ebs[i];
+  for (int i = tid; i < ED * XD; i += 128) sWg[i] = ew.eWg[i];
+  if (tid < XD) {
+    swd[tid] = ew.ewd[tid];
+    sbg[tid] = ew.ebg[tid];
+    float a = 0.f;
+    for (int h = 0; h < XD; ++h) a = fmaf(ew.eWu[h * XD + tid], ew.ewd[h], a);
+    sUd[tid] = a;
+  }
+  if (tid < 3) swf[tid] = ew.ewf[tid];
+  __syncthreads();
+  const long long g = (long long)blockIdx.x * 128 + tid;
+  float xiraw[3] = {0.f, 0.f, 0.f}, eraw = 0.f, f[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) f[q] = 0.f;
+  if (g < p.E) {
+    const int k = find_mol(p.edge_off, p.B, g);
+    const int loc = (int)(g - p.edge_off[k]);
+    const int a0 = p.act_off[k], na = p.act_off[k + 1] - a0;
+    const int a = loc / na, b = loc - a * na;
+    const int row = p.act_idx[a0 + a], col = p.act_idx[a0 + b];
+    float dv[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dv[q] = w.x_init[row * 3 + q] - w.x_init[col * 3 + q];
+    eraw = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+    unit3(dv, xiraw);
+    const float xr[3] = {w.x[row * 3], w.x[row * 3 + 1], w.x[row * 3 + 2]};
+    const float xc[3] = {w.x[col * 3], w.x[col * 3 + 1], w.x[col * 3 + 2]};
+    edge_frame(xr, xc, f);
+  }
+  float mg[KE];
+  mg[0] = eraw;
+#pragma unroll
+  for (int h = 0; h < XD; ++h) {
+    const float wd = swd[h];
+    mg[1 + h] = safe_norm3(wd * xiraw[0], wd * xiraw[1], wd * xiraw[2]);
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float wf = swf[ch];
+    const float v0 = wf * xiraw[0], v1 = wf * xiraw[1], v2 = wf * xiraw[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) mg[1 + XD + ch * 3 + a] = f[a * 3] * v0 + f[a * 3 + 1] * v1 + f[a * 3 + 2] * v2;
+  }
+  float S[ED];
+#pragma unroll
+  for (int o = 0; o < ED; ++o) S[o] = sbs[o];
+#pragma unroll
+  for (int k = 0; k < KE; ++k) {
+#pragma unroll
+    for (int o4 = 0; o4 < ED; o4 += 4) {
+      const float4 wv = *reinterpret_cast<const float4*>(&sWs[k * ED + o4]);
+      S[o4 + 0] = fmaf(mg[k], wv.x, S[o4 + 0]);
+      S[o4 + 1] = fmaf(mg[k], wv.y, S[o4 + 1]);
+      S[o4 + 2] = fmaf(mg[k], wv.z, S[o4 + 2]);
+      S[o4 + 3] = fmaf(mg[k], wv.w, S[o4 + 3]);
+    }
+  }
+  float gate[XD];
+#pragma unroll
+  for (int j = 0; j < XD; ++j) gate[j] = sbg[j];
+  float* eo = w.e + (size_t)g * ED;
+#pragma unroll
+  for (int o4 = 0; o4 < ED; o4 += 4) {
+    float4 sv;
+    sv.x = siluf_(S[o4 + 0]); sv.y = siluf_(S[o4 + 1]); sv.z = siluf_(S[o4 + 2]); sv.w = siluf_(S[o4 + 3]);
+    *reinterpret_cast<float4*>(eo + o4) = sv;
+    const float se[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j4 = 0; j4 < XD; j4 += 4) {
+        const float4 wg = *reinterpret_cast<const float4*>(&sWg[(o4 + i) * XD + j4]);
+        gate[j4 + 0] = fmaf(se[i], wg.x, gate[j4 + 0]);
+        gate[j4 + 1] = fmaf(se[i], wg.y, gate[j4 + 1]);
+        gate[j4 + 2] = fmaf(se[i], wg.z, gate[j4 + 2]);
+        gate[j4 + 3] = fmaf(se[i], wg.w, gate[j4 + 3]);
+      }
+  }
+  float xo[XD * 3];
+#pragma unroll
+  for (int j = 0; j < XD; ++j) {
+    const float s = sUd[j] * sigmoidf_(gate[j]);
+    xo[j * 3 + 0] = s * xiraw[0]; xo[j * 3 + 1] = s * xiraw[1]; xo[j * 3 + 2] = s * xiraw[2];
+  }
+  float* xop = w.xi + (size_t)g * (XD * 3);
+#pragma unroll
+  for (int c4 = 0; c4 < XD * 3; c4 += 4) *reinterpret_cast<float4*>(xop + c4) = make_float4(xo[c4], xo[c4 + 1], xo[c4 + 2], xo[c4 + 3]);
+  float* fo = w.frames + (size_t)g * 9;
+#pragma unroll
+  for (int q = 0; q < 9; ++q) fo[q] = f[q];
+}
+
 // ================================================================================= fused edge message
 struct EdgeSmem {
   float sA[TME][284];     // A operand: stage 0 [e | vn | q], stages 1..3 [m.s(256) | vn(8) | q(9) | pad]
@@ -793,7 +894,11 @@ void launch_prep(cudaStream_t st, const Plan& p, const Dims& d, const float* xh,
 }
 void launch_edge_embed(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const Work& w) {
   const unsigned tiles = (unsigned)((p.E + TME - 1) / TME);
-  if (tiles) k_edge_embed<<<tiles, kThreads, 0, st>>>(p, d, ew, w);
+  if (!tiles) return;
+  const unsigned blocks = (unsigned)((p.E + 127) / 128);
+  if (d.Ed == 64 && d.Xd == 16) k_edge_embed_tpe<64, 16><<<blocks, 128, 0, st>>>(p, ew, w);
+  else if (d.Ed == 16 && d.Xd == 8) k_edge_embed_tpe<16, 8><<<blocks, 128, 0, st>>>(p, ew, w);
+  else k_edge_embed<<<tiles, kThreads, 0, st>>>(p, d, ew, w);
 }
 void launch_node_embed(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerW& l0,
                        const Work& w) {
