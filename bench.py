@@ -190,6 +190,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the single JSON line (no "NCCL version ..." banner)
         dist.init_process_group("nccl", device_id=dev)
 
     batch, atoms = workload(args)
@@ -375,7 +376,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "molecules/s", "h2d_bytes_per_step": int(num_nodes_host.numel() * 8 +
                 (ctx_host.numel() * 4 if ctx_host is not None else 0)),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": 1000 * secs_e2e / args.steps},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * world,
         "clocks": clk,
         "roofline": roofline,
     }
