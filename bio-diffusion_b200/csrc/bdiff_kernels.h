@@ -24,6 +24,9 @@ struct Work {
   float* e;        // [E,Ed]
   float* xi;       // [E,Xd*3]
   float* frames;   // [E,9]
+  float* scrY;     // [N,256] exchange scratch of the clustered node pass (silu(FF hidden))
+  float* scrZ;     // [N,256] exchange scratch (FF output Z2)
+  float* scrDot;   // [N,8]   partial dot products of the position-gate
   int* nan_flag;
 };
 
@@ -61,6 +64,12 @@ void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, co
                          unsigned char* blob);
 void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
+size_t tc_node4_blob_bytes();
+cudaError_t tc_node4_configure();
+void launch_tc_pack_node4(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
+                          unsigned char* blob);
+void launch_node_update_tc4(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
+                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
 void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
 
 }  // namespace bdiff
