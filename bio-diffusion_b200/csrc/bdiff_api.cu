@@ -70,7 +70,7 @@ struct bdiff_handle {
   // tensor-core path state (bdiff_edge_tc.cu): per-layer pre-swizzled bf16 weight blobs
   DevBuf tc_blob, tc_node_blob;
   size_t tc_layer_bytes = 0, tc_node_layer_bytes = 0;
-  bool node_cluster = true;     // 4-CTA cluster split of the node pass (BDIFF_NODE_CLUSTER=0 selects the 1-CTA kernel)
+  bool node_cluster = false;    // BDIFF_NODE_CLUSTER=1: 4-CTA cluster split of the node pass (measured: no faster)
   bool tc_dirty = true;
   int num_sms = 148;
 
@@ -326,7 +326,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
     if (e == cudaSuccess) e = tc_node_configure();
     if (e == cudaSuccess) e = tc_node4_configure();
     const char* nc = getenv("BDIFF_NODE_CLUSTER");
-    h->node_cluster = !(nc && nc[0] == '0');
+    h->node_cluster = (nc && nc[0] == '1');
     h->tc_layer_bytes = tc_blob_bytes(d.Ed, d.Xd);
     h->tc_node_layer_bytes = h->node_cluster ? tc_node4_blob_bytes() : tc_node_blob_bytes();
     if (e == cudaSuccess) e = h->tc_blob.ensure(h->tc_layer_bytes * d.L);

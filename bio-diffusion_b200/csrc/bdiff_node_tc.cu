@@ -5,9 +5,9 @@
 // final scalar projection.  Tile = 128 nodes = the 128 TMEM lanes, a thread PAIR per node (half 0: accumulator
 // columns [0,128) / vector channels [0,16); half 1 the rest).  The A operand (bf16, K-major, 128B swizzle, 5
 // K-blocks) is rewritten in place between the chained GEMMs; weights stream from L2 as pre-swizzled bf16
-// K-blocks through a 2-stage TMA-bulk ring; the feed-forward vector gate  sigmoid(Wg Z2 + b)  gets its own small
-// N=32 MMA on the bf16 image of Z2 (folding it as Wg h_new - Wg h_old like in the edge kernel cancels badly here
-// because |h| >> |Z2| on the residual stream).
+// K-blocks through a 2-stage TMA-bulk ring; the feed-forward vector gate  sigmoid(Wg Z2 + b)  is folded into the
+// neighbouring GEMMs via  Wg Z2 = Wg h_new - Wg h_old  (A-negate), like in the edge kernel (a direct N=32 MMA on
+// Z2 was tried: same accuracy, one more phase).
 // TMEM columns: S 0..255 | U 256..287 | chi (96) 288..383 | VD_ff (48) 384..431 | pair exchange 2x40 432..511.
 #include "bdiff_kernels.h"
 #include "bdiff_tc.cuh"
@@ -17,18 +17,18 @@ namespace bdiff {
 constexpr int NT_EPI = 256;
 constexpr int NT_THREADS = NT_EPI + 64;
 constexpr int NTM = 128;
-constexpr int NRING = 256 * 128;
+constexpr int NRING = 288 * 128;
 constexpr int NSTAGES = 2;
 constexpr int NM_S = 0, NM_U = 256, NM_CHI = 288, NM_VDF = 384, NM_EX = 432;
 
-size_t tc_node_blob_bytes() { return (size_t)(4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + 8 * 256) * 128; }
+size_t tc_node_blob_bytes() { return (size_t)(4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + 8 * 256) * 128; }
 
 // Per-layer bf16 blob in streaming order:
-//   G1a 4x[256]: W1[:, 0:256]   | G1b 4x[256]: W1[:, 256:512]        | G1c [256]: W1[:, 512:544]
-//   G2  4x[256]: W2             | Gg 4x[32]: Wg_ff                    | G3a 4x[256]: Wp[:, 0:256] | G3b [256]: Wp[:, 256:288]
+//   G1a 4x[256]: W1[:, 0:256]   | G1b 4x[288]: W1[:, 256:512] + Wg_ff | G1c [256]: W1[:, 512:544]
+//   G2  4x[256]: W2             | G3a 4x[288]: Wp[:, 0:256] + Wg_ff   | G3b [256]: Wp[:, 256:288]
 //   not last: G4 4x[256]: next.Wsi, G5 4x[256]: next.Wsj            last: Gp 5x[32]: projection scalar_out
 __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last, unsigned char* __restrict__ blob) {
-  const long long total_rows = 4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + (last ? 5 * 32 : 8 * 256);
+  const long long total_rows = 4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + (last ? 5 * 32 : 8 * 256);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total_rows * 64) return;
   long long rowg = idx / 64;
@@ -45,9 +45,10 @@ __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last
   if (seg(4 * 256)) {
     const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
     v = lw.W1[(size_t)(j * 64 + kc) * 256 + r];
-  } else if (seg(4 * 256)) {
-    const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
-    v = lw.W1[(size_t)(256 + j * 64 + kc) * 256 + r];
+  } else if (seg(4 * 288)) {
+    const int j = (int)(rowg / 288); r = (int)(rowg % 288); base += (size_t)j * 288 * 128;
+    const int kk = j * 64 + kc;
+    v = r < 256 ? lw.W1[(size_t)(256 + kk) * 256 + r] : lw.Wgf[(size_t)kk * 32 + (r - 256)];
   } else if (seg(256)) {
     r = (int)rowg;
     const int kk = 512 + kc;
@@ -55,12 +56,10 @@ __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last
   } else if (seg(4 * 256)) {
     const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
     v = lw.W2[(size_t)(j * 64 + kc) * 256 + r];
-  } else if (seg(4 * 32)) {
-    const int j = (int)(rowg / 32); r = (int)(rowg % 32); base += (size_t)j * 32 * 128;
-    v = lw.Wgf[(size_t)(j * 64 + kc) * 32 + r];
-  } else if (seg(4 * 256)) {
-    const int j = (int)(rowg / 256); r = (int)(rowg % 256); base += (size_t)j * 256 * 128;
-    v = lw.Wp[(size_t)(j * 64 + kc) * 256 + r];
+  } else if (seg(4 * 288)) {
+    const int j = (int)(rowg / 288); r = (int)(rowg % 288); base += (size_t)j * 288 * 128;
+    const int kk = j * 64 + kc;
+    v = r < 256 ? lw.Wp[(size_t)kk * 256 + r] : lw.Wgf[(size_t)kk * 32 + (r - 256)];
   } else if (seg(256)) {
     r = (int)rowg;
     const int kk = 256 + kc;
@@ -104,11 +103,15 @@ constexpr size_t NT_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING +
 __device__ __forceinline__ void stage_rows(unsigned char* X, const float* __restrict__ base, int ld, int kk0, int wih,
                                            int lane) {
   const int kk = kk0 + lane * 4;
-#pragma unroll 4
-  for (int rr = wih; rr < NTM; rr += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)rr * ld + lane * 4);
-    *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(rr, kk & 63)) =
-        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {           // 16 independent 512-byte row loads in flight per warp
+    float4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = *reinterpret_cast<const float4*>(base + (size_t)(wih + 4 * (b * 16 + i)) * ld + lane * 4);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(wih + 4 * (b * 16 + i), kk & 63)) =
+          make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
   }
 }
 
@@ -163,10 +166,12 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
           off += bytes;
           ++ci;
         };
-        for (int j = 0; j < 9; ++j) push(256 * 128);      // G1a, G1b, G1c
+        for (int j = 0; j < 4; ++j) push(256 * 128);      // G1a
+        for (int j = 0; j < 4; ++j) push(288 * 128);      // G1b (+ gate rows)
+        push(256 * 128);                                  // G1c
         for (int j = 0; j < 4; ++j) push(256 * 128);      // G2
-        for (int j = 0; j < 4; ++j) push(32 * 128);       // Gg
-        for (int j = 0; j < 5; ++j) push(256 * 128);      // G3a, G3b
+        for (int j = 0; j < 4; ++j) push(288 * 128);      // G3a (+ gate rows)
+        push(256 * 128);                                  // G3b
         if (!last) { for (int j = 0; j < 8; ++j) push(256 * 128); }
         else { for (int j = 0; j < 5; ++j) push(32 * 128); }
       }
@@ -174,7 +179,8 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
   } else if (warp == 9) {
     // ======================================================================= MMA issuer (one lane)
     if (lane == 0) {
-      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false);
+      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
+                     i32n = umma_idesc_bf16(32, true);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0;
       auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
@@ -194,12 +200,15 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
           done_w();
         }
       };
-      auto gemm_gate = [&]() {             // U = Z2 . Wg^T (N=32), 4 chunks of 32 rows
+      auto gemm288 = [&](bool fresh_s, bool negate_u) {   // ... plus the 32 gate columns -> U (= +/- Wg . A)
         for (int j = 0; j < 4; ++j) {
           const uint32_t wb = wait_w();
-          for (int s = 0; s < 4; ++s)
-            umma_bf16(tmem + NM_U, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i32,
-                      (j | s) > 0);
+          for (int s = 0; s < 4; ++s) {
+            const uint64_t ad = umma_desc_sw128(xaddr + j * X_BLOCK + s * 32);
+            umma_bf16(tmem + NM_S, ad, umma_desc_sw128(wb + s * 32), i256, fresh_s ? (j | s) > 0 : true);
+            umma_bf16(tmem + NM_U, ad, umma_desc_sw128(wb + 256 * 128 + s * 32), negate_u ? i32n : i32,
+                      negate_u ? (j | s) > 0 : true);
+          }
           done_w();
         }
       };
@@ -211,10 +220,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G1a: agg_s . W1a
-        wait_a(); gemm256(false); gemm_extra(); umma_commit(&T.d_full);             // G1b/c: + h . W1b + [vn|q] . W1c
+        wait_a(); gemm288(false, true); gemm_extra(); umma_commit(&T.d_full);       // G1b/c: + h . W1b, U = -Wg h, + [vn|q] . W1c
         wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G2: Y . W2
-        wait_a(); gemm_gate(); umma_commit(&T.d_full);                              // Gg: U = Z2 . Wg
-        wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G3a: h_new . Wp
+        wait_a(); gemm288(true, false); umma_commit(&T.d_full);                     // G3a: h_new . Wp, U += Wg h_new
         wait_a(); gemm_extra(); umma_commit(&T.d_full);                             // G3b
         if (!last) {
           wait_a(); gemm256(true); umma_commit(&T.d_full);                          // G4: h_new . Wsi(next)
@@ -266,6 +274,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         for (int i = 0; i < 24; ++i) vdh[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; ++i) vdf[i] = 0.f;
+#pragma unroll 4
         for (int cc = 0; cc < 16; ++cc) {       // 4 channels (12 floats) at a time: [agg_v (32 ch) | chi (32 ch)]
           const float* src = cc < 8 ? ag + kH + cc * 12 : crow + (cc - 8) * 12;
           const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4),
@@ -340,31 +349,28 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
       }
       publish();
-      // ---- E2a: Z2 = S + b2 -> A blocks 0..3 (bf16) for the gate MMA; h_new = (h + Z2) * mask -> global h (fp32),
-      //      written through a per-warp 32x32 transpose so that every global access is a full 128-byte line
+      // ---- E2: h_new = (h + S + b2) * mask -> global h (fp32) through a per-warp 32x32 transpose (full 128-byte
+      //      lines) and, from the same loop, bf16 into A blocks 0..3
       wait_d();
       for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
         float v[32];
         tmem_ld32(tl + NM_S + c0, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(&sw.b2[c0 + q * 4]);
-          v[q * 4 + 0] += bb.x; v[q * 4 + 1] += bb.y; v[q * 4 + 2] += bb.z; v[q * 4 + 3] += bb.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
-#pragma unroll
         for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
         __syncwarp();
         float* hb = w.h + ((size_t)tile * NTM + row0) * kH + c0 + lane;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) hb[(size_t)i * kH] = (hb[(size_t)i * kH] + tw[i][lane]) * T.sMask[row0 + i];
+        const float b2v = sw.b2[c0 + lane];
+        float ho[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) ho[i] = hb[(size_t)i * kH];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float hn = (ho[i] + tw[i][lane] + b2v) * T.sMask[row0 + i];
+          hb[(size_t)i * kH] = hn;
+          x_store1(X, row0 + i, c0 + lane, hn);
+        }
         __syncwarp();
       }
-      publish();
-      // ---- E2b: after the gate MMA has consumed Z2, stage h_new (re-read in fp32) as the next A operand
-      wait_d();
-      stage_rows(X, w.h + (size_t)tile * NTM * kH + half * 128, kH, half * 128, wih, lane);
       publish();
       // ---- E3a: FF vector gate, chi_new for this half's 16 channels, vector_down of the position GCP
       wait_d();
@@ -609,7 +615,7 @@ cudaError_t tc_node_configure() {
 
 void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
                          unsigned char* blob) {
-  const long long rows = 4 * 256 + 4 * 256 + 256 + 4 * 256 + 4 * 32 + 4 * 256 + 256 + (last ? 5 * 32 : 8 * 256);
+  const long long rows = 4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + (last ? 5 * 32 : 8 * 256);
   const long long total = rows * 64;
   k_tc_pack_node<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lw, wn, ew, d, last, blob);
 }
@@ -726,11 +732,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void stage_rows_cg(unsigned char* X, const float* __restrict__ base, int ld, int kk0, int wih,
                                               int lane) {
   const int kk = kk0 + lane * 4;
-#pragma unroll 4
-  for (int rr = wih; rr < NTM; rr += 4) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(base + (size_t)rr * ld + lane * 4));
-    *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(rr, kk & 63)) =
-        make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    float4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      v[i] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(wih + 4 * (b * 16 + i)) * ld + lane * 4));
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(wih + 4 * (b * 16 + i), kk & 63)) =
+          make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
   }
 }
 
@@ -900,6 +911,7 @@ __global__ void __cluster_dims__(NCL, 1, 1) __launch_bounds__(NT_THREADS, 1)
         for (int i = 0; i < 24; ++i) vdh[i] = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; ++i) vdf[i] = 0.f;
+#pragma unroll 4
         for (int cc = 0; cc < 16; ++cc) {
           const float* src = cc < 8 ? ag + kH + cc * 12 : crow + (cc - 8) * 12;
           const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4),
