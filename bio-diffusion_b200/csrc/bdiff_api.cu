@@ -452,14 +452,25 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   // device layout: [mol_off | act_off | act_idx | node_mol | edge_off(int64) | mask]
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const long long ntile128 = (E + 127) / 128;
+  std::vector<int> tile_mol((size_t)ntile128 + 1, 0);
+  {
+    int k = 0;
+    for (long long t = 0; t < ntile128; ++t) {
+      const long long g = t * 128;
+      while (k < B && edge_off[k + 1] <= g) ++k;
+      tile_mol[(size_t)t] = k;
+    }
+  }
   const size_t o_mo = take((B + 1) * 4), o_ao = take((B + 1) * 4), o_ai = take((M + 1) * 4), o_nm = take(N * 4),
-               o_eo = take((B + 1) * 8), o_mk = take(N);
+               o_eo = take((B + 1) * 8), o_tm = take((ntile128 + 1) * 4), o_mk = take(N);
   std::vector<unsigned char> stage(off, 0);
   memcpy(stage.data() + o_mo, mol_off.data(), (B + 1) * 4);
   memcpy(stage.data() + o_ao, act_off.data(), (B + 1) * 4);
   if (M) memcpy(stage.data() + o_ai, act_idx.data(), M * 4);
   memcpy(stage.data() + o_nm, node_mol.data(), N * 4);
   memcpy(stage.data() + o_eo, edge_off.data(), (B + 1) * 8);
+  memcpy(stage.data() + o_tm, tile_mol.data(), (size_t)(ntile128 + 1) * 4);
   memcpy(stage.data() + o_mk, mk.data(), N);
   e = h->plan_buf.ensure(off);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->plan_buf.p, stage.data(), off, cudaMemcpyHostToDevice, st);
@@ -473,6 +484,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   p.act_idx = reinterpret_cast<int*>(base + o_ai);
   p.node_mol = reinterpret_cast<int*>(base + o_nm);
   p.edge_off = reinterpret_cast<long long*>(base + o_eo);
+  p.tile_mol = reinterpret_cast<int*>(base + o_tm);
   p.mask = base + o_mk;
   h->Npad = round_up(N, 128);
   h->Epad = (E + 127) / 128 * 128 + 128;

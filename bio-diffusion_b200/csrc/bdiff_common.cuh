@@ -33,6 +33,7 @@ struct Plan {
   const int* act_idx;    // [M]   global ids of unmasked nodes, ascending
   const long long* edge_off;  // [B+1] prefix of nact^2
   const int* node_mol;   // [N]   molecule of each node
+  const int* tile_mol;   // [ceil(E/128)] molecule that contains edge 128*t (start of the linear molecule search)
   const unsigned char* mask;  // [N]
 };
 
@@ -113,9 +114,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
-// for single helper threads that share a scheduler with compute warps: do not burn issue slots while waiting
+// for the single helper threads (TMA producer, MMA issuer): mbarrier.try_wait already suspends the warp in hardware
+// and wakes ~60 cycles after the arrive, so no software back-off (a __nanosleep here only adds hand-off latency)
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  while (!mbar_try_wait(bar, parity)) {
+  }
 }
 // TMA bulk copy global -> shared (SASS: UBLKCP), completion signalled on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -300,6 +303,13 @@ __device__ __forceinline__ int find_mol(const long long* __restrict__ edge_off, 
     else hi = mid;
   }
   return lo;
+}
+
+// Same result as find_mol, but a short forward scan from the tile's first molecule (1-3 dependent loads).
+__device__ __forceinline__ int find_mol_from(const long long* __restrict__ edge_off, int k0, long long g) {
+  int k = k0;
+  while (__ldg(edge_off + k + 1) <= g) ++k;
+  return k;
 }
 
 }  // namespace bdiff

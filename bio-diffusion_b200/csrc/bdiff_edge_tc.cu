@@ -187,7 +187,7 @@ __global__ void k_selftest_pack(const float* __restrict__ W, unsigned char* __re
 constexpr int TC_EPI = 256;
 constexpr int TC_THREADS2 = TC_EPI + 64;
 
-struct SmallW {            // fp32 copies of the thread-local (vector channel) weights, broadcast-read
+struct alignas(16) SmallW {   // fp32 copies of the thread-local (vector channel) weights, broadcast-read
   float Wd0x[16 * 20];     // [Xd][hid0]
   float Wf0x[16 * 3];      // [Xd][3]
   float Wu0[20 * 32];      // [hid0][32]
@@ -205,7 +205,7 @@ struct TcSmemTail {
   SmallW sw;
   float sAttn[2][TMT];
   int sRow[TMT], sCol[TMT], sB[TMT], sNa[TMT];
-  uint64_t full[2], empty[2], a_ready, d_full;
+  uint64_t full[2], empty[2], a_ready, d_full, wbar;
   uint32_t tmem_ptr;
 };
 
@@ -299,24 +299,28 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(&T.tmem_ptr, 512);
-  {
+  // small (vector-channel) weights -> shared memory: one TMA bulk copy per array, all in flight at once
+  // (every packed array starts 256-byte aligned and is padded, so sizes are rounded up to 16 bytes)
+  if (tid == 0) {
+    mbar_init(&T.wbar, 1);
+    mbar_fence_init();
     SmallW& s = T.sw;
-    for (int i = tid; i < XD * HID0; i += TC_THREADS2) s.Wd0x[i] = lw.Wd0x[i];
-    for (int i = tid; i < XD * 3; i += TC_THREADS2) s.Wf0x[i] = lw.Wf0x[i];
-    for (int i = tid; i < HID0 * 32; i += TC_THREADS2) s.Wu0[i] = lw.Wu0[i];
+    auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
+    mbar_expect_tx(&T.wbar, sz(XD * HID0) + sz(XD * 3) + sz(HID0 * 32) +
+                                3 * (sz(256) + sz(256) + sz(256) + sz(96) + sz(32)) + sz(32) + sz(256) + sz(1));
+    auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &T.wbar); };
+    cp(s.Wd0x, lw.Wd0x, XD * HID0); cp(s.Wf0x, lw.Wf0x, XD * 3); cp(s.Wu0, lw.Wu0, HID0 * 32);
     for (int k = 0; k < 3; ++k) {
-      for (int i = tid; i < 256; i += TC_THREADS2) { s.Wdk[k][i] = lw.Wdk[k][i]; s.Wuk[k][i] = lw.Wuk[k][i]; s.bk[k][i] = lw.bk[k][i]; }
-      for (int i = tid; i < 96; i += TC_THREADS2) s.Wfk[k][i] = lw.Wfk[k][i];
-      for (int i = tid; i < 32; i += TC_THREADS2) s.bg[k + 1][i] = lw.bgk[k][i];
+      cp(s.Wdk[k], lw.Wdk[k], 256); cp(s.Wuk[k], lw.Wuk[k], 256); cp(s.bk[k], lw.bk[k], 256);
+      cp(s.Wfk[k], lw.Wfk[k], 96); cp(s.bg[k + 1], lw.bgk[k], 32);
     }
-    for (int i = tid; i < 32; i += TC_THREADS2) s.bg[0][i] = lw.bg0[i];
-    for (int i = tid; i < 256; i += TC_THREADS2) s.wa[i] = lw.wa[i];
-    if (tid == 0) s.ba[0] = lw.ba[0];
+    cp(s.bg[0], lw.bg0, 32); cp(s.wa, lw.wa, 256); cp(s.ba, lw.ba, 1);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = T.tmem_ptr;
+  if (warp < 8) mbar_wait(&T.wbar, 0);      // small weights have landed (only the compute warps read them)
 
   if (warp == 8) {
     // ===================================================================== TMA producer (one lane)
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
       const long long g = (long long)tile * TMT + r;
       int row = -1, col = -1, b = 0, na = 0;
       if (g < p.E) {
-        const int k = find_mol(p.edge_off, p.B, g);
+        const int k = find_mol_from(p.edge_off, __ldg(p.tile_mol + tile), g);
         const int loc = (int)(g - p.edge_off[k]);
         const int a0 = p.act_off[k];
         na = p.act_off[k + 1] - a0;

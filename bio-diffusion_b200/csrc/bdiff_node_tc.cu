@@ -78,7 +78,7 @@ __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last
   *reinterpret_cast<__nv_bfloat16*>(blob + base + sw128_offset(r, kc)) = __float2bfloat16_rn(v);
 }
 
-struct SmallWN {
+struct alignas(16) SmallWN {
   float Wdf[64 * 16], Wff[64 * 3], Wuf[16 * 32], bgf[32];
   float b1[256], b2[256];
   float Wdp[32 * 8], Wfp[32 * 3], Wup[8], bp[256], wgp[256], bgp[4];
@@ -92,7 +92,7 @@ struct NodeTcTail {
   float sTw[8][32][33];    // per-warp 32x32 transposition scratch (coalesced global stores of accumulator tiles)
   float sMask[NTM];
   float sDot[2][NTM];
-  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full;
+  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full, wbar;
   uint32_t tmem_ptr;
 };
 
@@ -133,9 +133,17 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(&T.tmem_ptr, 512);
-  {
+  // small weights -> shared memory by TMA bulk copies (all in flight at once; sizes rounded up to 16 bytes, every
+  // packed array is 256-byte aligned and padded)
+  if (tid == 0) {
+    mbar_init(&T.wbar, 1);
+    mbar_fence_init();
     SmallWN& s = T.sw;
-    auto cp = [&](float* dst, const float* src, int n) { for (int i = tid; i < n; i += NT_THREADS) dst[i] = src[i]; };
+    auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
+    uint32_t total = sz(1024) + sz(192) + sz(512) + sz(32) + 2 * sz(256) + sz(256) + sz(96) + sz(8) + 2 * sz(256) + sz(1);
+    total += last ? sz(1024) + sz(96) + sz(d.Hin) : sz(256) + 2 * sz(32 * hid0) + 2 * sz(96);
+    mbar_expect_tx(&T.wbar, total);
+    auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &T.wbar); };
     cp(s.Wdf, lw.Wdf, 64 * 16); cp(s.Wff, lw.Wff, 64 * 3); cp(s.Wuf, lw.Wuf, 16 * 32); cp(s.bgf, lw.bgf, 32);
     cp(s.b1, lw.b1, 256); cp(s.b2, lw.b2, 256);
     cp(s.Wdp, lw.Wdp, 32 * 8); cp(s.Wfp, lw.Wfp, 32 * 3); cp(s.Wup, lw.Wup, 8); cp(s.bp, lw.bp, 256);
@@ -151,6 +159,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = T.tmem_ptr;
+  if (warp < 8) mbar_wait(&T.wbar, 0);
 
   if (warp == 8) {
     // ===================================================================== TMA producer (one lane)
@@ -691,7 +700,7 @@ struct Node4Tail {
   SmallWN sw;
   float sTw[8][32][33];
   float sMask[NTM];
-  uint64_t full[N4_NST], empty[N4_NST], a_ready, d_full, cbar;
+  uint64_t full[N4_NST], empty[N4_NST], a_ready, d_full, cbar, wbar;
   uint32_t tmem_ptr;
 };
 constexpr size_t N4_SMEM_BYTES = 5 * (size_t)X_BLOCK + N4_NST * (size_t)N4_STAGE + sizeof(Node4Tail) + 1024;
@@ -767,9 +776,17 @@ __global__ void __cluster_dims__(NCL, 1, 1) __launch_bounds__(NT_THREADS, 1)
     mbar_fence_init();
   }
   if (warp == 8) tmem_alloc(&T.tmem_ptr, 512);
-  {
+  // small weights -> shared memory by TMA bulk copies (all in flight at once; sizes rounded up to 16 bytes, every
+  // packed array is 256-byte aligned and padded)
+  if (tid == 0) {
+    mbar_init(&T.wbar, 1);
+    mbar_fence_init();
     SmallWN& s = T.sw;
-    auto cp = [&](float* dst, const float* src, int n) { for (int i = tid; i < n; i += NT_THREADS) dst[i] = src[i]; };
+    auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
+    uint32_t total = sz(1024) + sz(192) + sz(512) + sz(32) + 2 * sz(256) + sz(256) + sz(96) + sz(8) + 2 * sz(256) + sz(1);
+    total += last ? sz(1024) + sz(96) + sz(d.Hin) : sz(256) + 2 * sz(32 * hid0) + 2 * sz(96);
+    mbar_expect_tx(&T.wbar, total);
+    auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &T.wbar); };
     cp(s.Wdf, lw.Wdf, 64 * 16); cp(s.Wff, lw.Wff, 64 * 3); cp(s.Wuf, lw.Wuf, 16 * 32); cp(s.bgf, lw.bgf, 32);
     cp(s.b1, lw.b1, 256); cp(s.b2, lw.b2, 256);
     cp(s.Wdp, lw.Wdp, 32 * 8); cp(s.Wfp, lw.Wfp, 32 * 3); cp(s.Wup, lw.Wup, 8); cp(s.bp, lw.bp, 256);
@@ -786,6 +803,7 @@ __global__ void __cluster_dims__(NCL, 1, 1) __launch_bounds__(NT_THREADS, 1)
   tc_fence_after();
   cluster_barrier_all();          // every CTA's mbarriers are initialised before anybody arrives remotely
   const uint32_t tmem = T.tmem_ptr;
+  if (warp < 8) mbar_wait(&T.wbar, 0);
 
   if (warp == 8) {
     if (lane == 0) {
