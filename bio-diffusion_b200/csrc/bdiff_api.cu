@@ -65,6 +65,7 @@ struct bdiff_handle {
   DevBuf work_buf;
   Work work{};
   DevBuf eps_buf;      // [N,3+F] denoiser output inside reverse_step / decode
+  DevBuf dbg_buf;      // clock64 stamps (BDIFF_TIMING=1)
   DevBuf tu_buf;       // uniform t scalar
 
   // tensor-core path state (bdiff_edge_tc.cu): per-layer pre-swizzled bf16 weight blobs
@@ -250,6 +251,12 @@ cudaError_t ensure_work(bdiff_handle* h) {
   w.h = b + o_h; w.chi = b + o_chi; w.PI = b + o_PI; w.PJ = b + o_PJ; w.agg = b + o_agg; w.hproj = b + o_hp;
   w.e = b + o_e; w.xi = b + o_xie; w.frames = b + o_fr; w.scrY = b + o_sy; w.scrZ = b + o_sz; w.scrDot = b + o_sd;
   w.nan_flag = reinterpret_cast<int*>(b + o_flag);
+  w.dbg = nullptr;
+  if (getenv("BDIFF_TIMING")) {
+    e = h->dbg_buf.ensure(256 * 64 * sizeof(long long));
+    if (e != cudaSuccess) return e;
+    w.dbg = static_cast<long long*>(h->dbg_buf.p);
+  }
   e = h->eps_buf.ensure(Np * (3 + d.F) * sizeof(float));
   if (e != cudaSuccess) return e;
   return h->tu_buf.ensure(256);
@@ -605,6 +612,7 @@ int32_t bdiff_debug_tap(bdiff_handle* h, void* stream, const char* which, float*
   else if (s == "x") { src = w.x; *rows = N; *cols = 3; }
   else if (s == "fbar") { src = w.fbar; *rows = N; *cols = 12; }
   else if (s == "chi_in") { src = w.chi_in; *rows = N; *cols = 6; }
+  else if (s == "dbg" && w.dbg) { src = reinterpret_cast<const float*>(w.dbg); *rows = 256; *cols = 128; }
   else return h->fail(BDIFF_EINVAL, "unknown tap '%s'", which);
   if (dst && *rows * *cols > 0) {
     cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)(*rows) * (*cols) * sizeof(float), cudaMemcpyDeviceToDevice,

@@ -18,6 +18,10 @@
 
 namespace bdiff {
 
+#ifndef BDIFF_STAMP
+#define BDIFF_STAMP(slot) do { if (w.dbg && (slot) < 64) w.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#endif
+
 constexpr int TC_THREADS = 192;
 constexpr int TMT = 128;                 // edges per tile
 constexpr int RING_STAGE = 320 * 128;    // bytes of the largest weight chunk (320 rows x 64 bf16)
@@ -418,9 +422,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
     float* exch_mine = &T.sT[half][r][0];
     const float* exch_other = &T.sT[half ^ 1][r][0];
     uint32_t pd = 0;
-    auto wait_d = [&]() { mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); };
-    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); };
+    int es = 0;
+    auto wait_d = [&]() { if (tid == 0) BDIFF_STAMP(es++); mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); if (tid == 0) BDIFF_STAMP(es++); };
+    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); if (tid == 0) BDIFF_STAMP(es++); };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tid == 0) BDIFF_STAMP(es++);
       const long long g = (long long)tile * TMT + r;
       int row = -1, col = -1, b = 0, na = 0;
       if (g < p.E) {
@@ -670,6 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
         named_bar_sync(1 + half, TMT);
       }
       named_bar_sync(3, TC_EPI);       // sRow / exchange buffers free for the next tile
+      if (tid == 0) BDIFF_STAMP(es++);
     }
     tc_fence_before();
   }

@@ -28,6 +28,7 @@ struct Work {
   float* scrZ;     // [N,256] exchange scratch (FF output Z2)
   float* scrDot;   // [N,8]   partial dot products of the position-gate
   int* nan_flag;
+  long long* dbg;  // optional [CTA][64] clock64 stamps of the tensor-core kernels (BDIFF_TIMING=1), else nullptr
 };
 
 cudaError_t configure_kernels();

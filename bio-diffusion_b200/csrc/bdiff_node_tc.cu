@@ -14,6 +14,10 @@
 
 namespace bdiff {
 
+#ifndef BDIFF_STAMP
+#define BDIFF_STAMP(slot) do { if (w.dbg && (slot) < 64) w.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#endif
+
 constexpr int NT_EPI = 256;
 constexpr int NT_THREADS = NT_EPI + 64;
 constexpr int NTM = 128;
@@ -192,7 +196,8 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
                      i32n = umma_idesc_bf16(32, true);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0;
-      auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
+      int ms = 32;
+      auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); BDIFF_STAMP(ms++); };
       auto wait_w = [&]() -> uint32_t {
         const uint32_t s = ci % NSTAGES;
         mbar_wait_backoff(&T.full[s], (ci / NSTAGES) & 1);
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         return raddr + s * NRING;
       };
       auto done_w = [&]() { umma_commit(&T.empty[ci % NSTAGES]); ++ci; };
+      auto stamp_commit = [&]() { BDIFF_STAMP(ms++); };
       auto gemm256 = [&](bool fresh) {     // 4 K-blocks of X against 4 chunks of 256 rows -> S
         for (int j = 0; j < 4; ++j) {
           const uint32_t wb = wait_w();
@@ -228,14 +234,14 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         done_w();
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G1a: agg_s . W1a
-        wait_a(); gemm288(false, true); gemm_extra(); umma_commit(&T.d_full);       // G1b/c: + h . W1b, U = -Wg h, + [vn|q] . W1c
-        wait_a(); gemm256(true); umma_commit(&T.d_full);                            // G2: Y . W2
-        wait_a(); gemm288(true, false); umma_commit(&T.d_full);                     // G3a: h_new . Wp, U += Wg h_new
-        wait_a(); gemm_extra(); umma_commit(&T.d_full);                             // G3b
+        wait_a(); gemm256(true); umma_commit(&T.d_full); stamp_commit();                            // G1a: agg_s . W1a
+        wait_a(); gemm288(false, true); gemm_extra(); umma_commit(&T.d_full); stamp_commit();       // G1b/c: + h . W1b, U = -Wg h, + [vn|q] . W1c
+        wait_a(); gemm256(true); umma_commit(&T.d_full); stamp_commit();                            // G2: Y . W2
+        wait_a(); gemm288(true, false); umma_commit(&T.d_full); stamp_commit();                     // G3a: h_new . Wp, U += Wg h_new
+        wait_a(); gemm_extra(); umma_commit(&T.d_full); stamp_commit();                             // G3b
         if (!last) {
-          wait_a(); gemm256(true); umma_commit(&T.d_full);                          // G4: h_new . Wsi(next)
-          wait_a(); gemm256(true); umma_commit(&T.d_full);                          // G5: h_new . Wsj(next)
+          wait_a(); gemm256(true); umma_commit(&T.d_full); stamp_commit();                          // G4: h_new . Wsi(next)
+          wait_a(); gemm256(true); umma_commit(&T.d_full); stamp_commit();                          // G5: h_new . Wsj(next)
         } else {
           wait_a();                                                                 // Gp: [h_new | vn | q] . Wproj -> U
           for (int j = 0; j < 5; ++j) {
@@ -246,7 +252,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
                         (j | s) > 0);
             done_w();
           }
-          umma_commit(&T.d_full);
+          umma_commit(&T.d_full); stamp_commit();
         }
       }
     }
@@ -256,9 +262,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const SmallWN& sw = T.sw;
     uint32_t pd = 0;
-    auto wait_d = [&]() { mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); };
-    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); };
+    int es = 0;
+    auto wait_d = [&]() { if (tid == 0) BDIFF_STAMP(es++); mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); if (tid == 0) BDIFF_STAMP(es++); };
+    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); if (tid == 0) BDIFF_STAMP(es++); };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tid == 0) BDIFF_STAMP(es++);
       const int node = tile * NTM + r;
       const bool valid = node < p.N;
       const float m = (valid && p.mask[node]) ? 1.f : 0.f;
