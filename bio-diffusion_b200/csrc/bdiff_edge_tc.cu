@@ -229,11 +229,21 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
   }
   for (int oc = half * 2; oc < half * 2 + 2; ++oc) {
     float u[8], mv[24];
-    tmem_ld8(tl + ucol + oc * 8, u);
-    if (!FIRST) {
-      tmem_ld8(tl + TM_MV + oc * 24, mv);
-      tmem_ld8(tl + TM_MV + oc * 24 + 8, mv + 8);
-      tmem_ld8(tl + TM_MV + oc * 24 + 16, mv + 16);
+    {
+      uint32_t ru[8], rm[24];
+      tmem_ld8_nw(tl + ucol + oc * 8, ru);
+      if (!FIRST) {
+        tmem_ld8_nw(tl + TM_MV + oc * 24, rm);
+        tmem_ld8_nw(tl + TM_MV + oc * 24 + 8, rm + 8);
+        tmem_ld8_nw(tl + TM_MV + oc * 24 + 16, rm + 16);
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = __uint_as_float(ru[i]);
+      if (!FIRST) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) mv[i] = __uint_as_float(rm[i]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -250,9 +260,7 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
       if (FIRST) { mv[j * 3] = s0 * g; mv[j * 3 + 1] = s1 * g; mv[j * 3 + 2] = s2 * g; }
       else { mv[j * 3] = fmaf(s0, g, mv[j * 3]); mv[j * 3 + 1] = fmaf(s1, g, mv[j * 3 + 1]); mv[j * 3 + 2] = fmaf(s2, g, mv[j * 3 + 2]); }
     }
-    tmem_st8(tl + TM_MV + oc * 24, mv);
-    tmem_st8(tl + TM_MV + oc * 24 + 8, mv + 8);
-    tmem_st8(tl + TM_MV + oc * 24 + 16, mv + 16);
+    tmem_st8xN<3>(tl + TM_MV + oc * 24, mv);      // completion awaited once, at the end of the function
     if (!LAST) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -275,6 +283,7 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
       }
     }
   }
+  tmem_st_wait();
 }
 
 template <int ED, int XD>
@@ -484,8 +493,8 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
 #pragma unroll
         for (int h = 0; h < H2; ++h)
           x_store1(X, r, ED + half * H2 + h, safe_norm3(vdh[h * 3], vdh[h * 3 + 1], vdh[h * 3 + 2]));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_st8(tl + TM_VD0 + half * 32 + q * 8, vdh + q * 8);
+        tmem_st8xN<4>(tl + TM_VD0 + half * 32, vdh);
+        tmem_st_wait();
         if (half == 0) {
           // vector_down_frames of GCP 0 and its scalarisation q0 (9 values), plus the zero padding
           float vdf0[9];
@@ -514,11 +523,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
 
       // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col]), this half's 128 columns
       wait_d();
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-        float v[32];
-        tmem_ld32(tl + TM_S + c0, v);
+      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64) {
+        float v[64];
+        tmem_ld64(tl + TM_S + c0, v);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 16; ++q) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
           if (row >= 0) {
             a = *reinterpret_cast<const float4*>(pi + c0 + q * 4);
@@ -530,7 +539,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
           v[q * 4 + 3] = silu_fast(v[q * 4 + 3] + a.w + bq.w);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
+        for (int q = 0; q < 8; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
       }
       publish();
 
@@ -543,9 +552,9 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
         if (k == 1) {
           float vd0[HID0 * 3];
           {
-            float t0[32], t1[32];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { tmem_ld8(tl + TM_VD0 + q * 8, t0 + q * 8); tmem_ld8(tl + TM_VD0 + 32 + q * 8, t1 + q * 8); }
+            float t0[64];
+            float* t1 = t0 + 32;
+            tmem_ld64(tl + TM_VD0, t0);
 #pragma unroll
             for (int i = 0; i < H2 * 3; ++i) { vd0[i] = t0[i]; vd0[H2 * 3 + i] = t1[i]; }
           }
@@ -584,11 +593,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
         publish();
         // ---- E(k)b: m_k = m_{k-1} + silu(S_k + b_k), this half's 128 columns
         wait_d();
-        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-          float v[32];
-          tmem_ld32(tl + TM_S + c0, v);
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64) {
+          float v[64];
+          tmem_ld64(tl + TM_S + c0, v);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 8; ++q) {
             float m[8];
             x_load8(X, r, c0 + q * 8, m);
             const float4 b0 = *reinterpret_cast<const float4*>(&sw.bk[k - 1][c0 + q * 8]);

@@ -323,8 +323,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
 #pragma unroll
         for (int h = 0; h < 8; ++h)
           x_store1(X, r, 256 + half * 8 + h, safe_norm3(vdh[h * 3], vdh[h * 3 + 1], vdh[h * 3 + 2]));
-#pragma unroll
-        for (int q = 0; q < 3; ++q) tmem_st8(tl + NM_VDF + half * 24 + q * 8, vdh + q * 8);
+        tmem_st8xN<3>(tl + NM_VDF + half * 24, vdh);
         if (half == 0) {
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch)
@@ -336,13 +335,16 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
           for (int i = 25; i < 32; ++i) x_store1(X, r, 256 + i, 0.f);
         }
         // own 16 chi channels -> TMEM scratch (needed for the residual in E3a)
+        {
+          float cown[48];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const float4 a = *reinterpret_cast<const float4*>(crow + half * 48 + q * 8);
-          const float4 b = *reinterpret_cast<const float4*>(crow + half * 48 + q * 8 + 4);
-          const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          tmem_st8(tl + NM_CHI + half * 48 + q * 8, v);
+          for (int q = 0; q < 12; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(crow + half * 48 + q * 4);
+            cown[q * 4] = a.x; cown[q * 4 + 1] = a.y; cown[q * 4 + 2] = a.z; cown[q * 4 + 3] = a.w;
+          }
+          tmem_st8xN<6>(tl + NM_CHI + half * 48, cown);
         }
+        tmem_st_wait();
       }
       publish();
       // ---- T0b: h -> A blocks 0..3 (after G1a has consumed agg_s)
@@ -394,12 +396,20 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       float vdp[24], vdfp[9];
       {
         float vdff[48], u[16], co[48], part[40];
+        {
+          uint32_t r0[48], r1[16], r2[48];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) tmem_ld8(tl + NM_VDF + q * 8, vdff + q * 8);
-        tmem_ld8(tl + NM_U + half * 16, u);
-        tmem_ld8(tl + NM_U + half * 16 + 8, u + 8);
+          for (int q = 0; q < 6; ++q) tmem_ld8_nw(tl + NM_VDF + q * 8, r0 + q * 8);
+          tmem_ld8_nw(tl + NM_U + half * 16, r1);
+          tmem_ld8_nw(tl + NM_U + half * 16 + 8, r1 + 8);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) tmem_ld8(tl + NM_CHI + half * 48 + q * 8, co + q * 8);
+          for (int q = 0; q < 6; ++q) tmem_ld8_nw(tl + NM_CHI + half * 48 + q * 8, r2 + q * 8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 48; ++i) { vdff[i] = __uint_as_float(r0[i]); co[i] = __uint_as_float(r2[i]); }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = __uint_as_float(r1[i]);
+        }
 #pragma unroll
         for (int i = 0; i < 40; ++i) part[i] = 0.f;
 #pragma unroll
@@ -434,21 +444,17 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
             part[24 + q * 3 + 2] = fmaf(wf, c2v, part[24 + q * 3 + 2]);
           }
         }
+        tmem_st8xN<6>(tl + NM_CHI + half * 48, co);
+        tmem_st8xN<5>(tl + NM_EX + half * 40, part);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          tmem_st8(tl + NM_CHI + half * 48 + q * 8, co + q * 8);
-          *reinterpret_cast<float4*>(crow + half * 48 + q * 8) = make_float4(co[q * 8], co[q * 8 + 1], co[q * 8 + 2], co[q * 8 + 3]);
-          *reinterpret_cast<float4*>(crow + half * 48 + q * 8 + 4) =
-              make_float4(co[q * 8 + 4], co[q * 8 + 5], co[q * 8 + 6], co[q * 8 + 7]);
-        }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) tmem_st8(tl + NM_EX + half * 40 + q * 8, part + q * 8);
+        for (int q = 0; q < 12; ++q)
+          *reinterpret_cast<float4*>(crow + half * 48 + q * 4) = make_float4(co[q * 4], co[q * 4 + 1], co[q * 4 + 2], co[q * 4 + 3]);
+        tmem_st_wait();
         tc_fence_before();
         named_bar_sync(3, NT_EPI);
         tc_fence_after();
         float other[40];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) tmem_ld8(tl + NM_EX + (half ^ 1) * 40 + q * 8, other + q * 8);
+        tmem_ld8xN<5>(tl + NM_EX + (half ^ 1) * 40, other);
 #pragma unroll
         for (int i = 0; i < 24; ++i) vdp[i] = part[i] + other[i];
 #pragma unroll
@@ -507,8 +513,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       if (last) {
         // projection GCP2 (256,32)->(Hin,0): [vn(32) | q(9) | 0] -> A block 4 columns 0..47
         float chi[96];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) tmem_ld8(tl + NM_CHI + q * 8, chi + q * 8);
+        tmem_ld8xN<12>(tl + NM_CHI, chi);
         for (int h = half * 16; h < half * 16 + 16; ++h) {
           float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -557,8 +562,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         publish();
         {
           float chi[96];
-#pragma unroll
-          for (int q = 0; q < 12; ++q) tmem_ld8(tl + NM_CHI + q * 8, chi + q * 8);
+          tmem_ld8xN<12>(tl + NM_CHI, chi);
           float* vrow = (half == 0 ? w.PI : w.PJ) + (size_t)node * kPStride + kH;
           const float* Wd = half == 0 ? sw.Wd0i : sw.Wd0j;
           const float* Wf = half == 0 ? sw.Wf0i : sw.Wf0j;
