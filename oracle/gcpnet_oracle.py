@@ -486,3 +486,103 @@ class RecordedNoise:
         self.i += 1
         assert tuple(t.shape) == tuple(shape), (t.shape, shape)
         return t
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation NLL (forward only): the loss terms of EquivariantVariationalDiffusion in eval mode
+# ----------------------------------------------------------------------------------------------
+def _cdf_std_gaussian(x: torch.Tensor) -> torch.Tensor:
+    return 0.5 * (1.0 + torch.erf(x / math.sqrt(2)))            # variational_diffusion.py:395-396
+
+
+def eval_nll(sd, cfg: OracleConfig, batch_index: torch.Tensor, mask: torch.Tensor, x: torch.Tensor,
+             one_hot: torch.Tensor, charges: torch.Tensor, context: Optional[torch.Tensor],
+             n_nodes_hist: Dict[int, int], randn: NoiseFn, t_int: Optional[torch.Tensor] = None,
+             denoise: Optional[Callable] = None):
+    """NLL per molecule in evaluation mode (two denoiser calls) + its terms.
+
+    Restates EquivariantVariationalDiffusion.atom_types_and_coords_forward with self.training == False
+    (variational_diffusion.py:955-1160: normalize :702-732, compute_noised_representation :910-931,
+    compute_kl_prior :501-556, log_pxh_given_z0_without_constants :598-699, log_constants_p_x_given_z0 :579-595,
+    delta_log_px :950-952, log_pN :932-940) and the evaluation branch of the Lightning module's assembly
+    (qm9_mol_gen_ddpm.py:184-262).  `x` must already be CoG-free (the module centralises first, :196-202).
+    RNG order: t_int ~ randint(1, T+1) [unless given], then randn(N,3), randn(N,F) for z_t, then again for z_0.
+    `denoise(batch_index, mask, z, t_nodes, context)` defaults to the oracle denoiser.
+    """
+    T = cfg.num_timesteps
+    nmol = int(batch_index.max().item()) + 1
+    mf = mask.float()
+    gamma = gamma_table(T, cfg.noise_precision, cfg.schedule_power)
+    if denoise is None:
+        denoise = lambda bi, mk, z, tn, ctx: denoiser_forward(sd, cfg, bi, mk, z, tn, ctx)
+    # normalize (:702-732)
+    xn = x / cfg.norm_values[0]
+    h_cat = (one_hot.float() - cfg.norm_biases[1]) / cfg.norm_values[1] * mf[:, None]
+    h_int = (charges.float() - cfg.norm_biases[2]) / cfg.norm_values[2]
+    if cfg.include_charges:
+        h_int = h_int * mf.reshape(h_int.shape[0], *([1] * (h_int.dim() - 1)))
+    num_nodes = torch.zeros(nmol, dtype=torch.long).index_add_(0, batch_index, mask.long())
+    sub_d = ((num_nodes - 1) * 3).float()                                       # subspace_dimensionality :492-498
+    delta_log_px = -sub_d * math.log(cfg.norm_values[0])                        # :950-952
+    if t_int is None:
+        t_int = torch.randint(1, T + 1, size=(nmol, 1))                         # eval: lowest_t = 1 (:986-991)
+    s_int = t_int - 1
+    s, t = s_int / T, t_int / T
+    g_s = gamma[torch.round(s * T).long()]                                      # [B,1]
+    g_t = gamma[torch.round(t * T).long()]
+    xh = torch.cat([xn, h_cat] + ([h_int.reshape(-1, 1)] if cfg.include_charges else []), dim=-1)
+    alpha = lambda g: torch.sqrt(torch.sigmoid(-g))
+    sigma = lambda g: torch.sqrt(torch.sigmoid(g))
+    eps_t = combined_noise(randn, cfg, batch_index, mask, nmol)
+    z_t = alpha(g_t)[batch_index] * xh + sigma(g_t)[batch_index] * eps_t        # :910-931
+    ctx = context
+    net_out = denoise(batch_index, mask, z_t, t[batch_index], ctx)
+    sum_mol = lambda v: torch.zeros(nmol).index_add_(0, batch_index, v.sum(-1))  # sum_node_features_except_batch
+    error_t = sum_mol((eps_t - net_out) ** 2)                                   # :1052
+    snr_weight = (torch.exp(-(g_s - g_t)) - 1).squeeze(-1)                      # :1057-1058
+    g0 = gamma[0]
+    neg_log_constants = -(sub_d * (-(0.5 * g0) - 0.5 * math.log(2 * math.pi)))  # :579-595,1062-1066
+    # KL prior (:501-556)
+    g_T = gamma[T]
+    mu_T = alpha(g_T) * xh
+    sig_T = sigma(g_T)
+    kl = lambda mu2, qs, d: d * torch.log(1.0 / qs) + 0.5 * (d * qs ** 2 + mu2) - 0.5 * d     # gaussian_KL, p_sigma = 1
+    kl_x = kl(sum_mol(mu_T[:, :3] ** 2), sig_T, sub_d)
+    kl_h = kl(sum_mol((mu_T[:, 3:] ** 2) * mf[:, None]), sig_T, 1)
+    kl_prior = kl_x + kl_h
+    # L0 at t = 0 with fresh noise (:1104-1132)
+    eps_0 = combined_noise(randn, cfg, batch_index, mask, nmol)
+    z_0 = alpha(g0) * xh + sigma(g0) * eps_0
+    net_0 = denoise(batch_index, mask, z_0, torch.zeros((xh.shape[0], 1)), ctx)
+    loss_0_x = 0.5 * sum_mol((eps_0[:, :3] - net_0[:, :3]) ** 2)                # -log p(x|z0) w/o constants (:611-622)
+    a = cfg.num_atom_types
+    sig0 = sigma(g0)
+    est_cat = z_0[:, 3:3 + a] * cfg.norm_values[1] + cfg.norm_biases[1]
+    onehot_u = h_cat * cfg.norm_values[1] + cfg.norm_biases[1]
+    cen = est_cat - 1
+    log_prop = torch.log(_cdf_std_gaussian((cen + 0.5) / (sig0 * cfg.norm_values[1]))
+                         - _cdf_std_gaussian((cen - 0.5) / (sig0 * cfg.norm_values[1])) + 1e-10)
+    log_prob = log_prop - torch.logsumexp(log_prop, dim=-1, keepdim=True)
+    log_ph_cat = sum_mol(log_prob * onehot_u * mf[:, None])
+    if cfg.include_charges:
+        h_integer = torch.round(h_int.reshape(-1, 1) * cfg.norm_values[2] + cfg.norm_biases[2]).long()
+        est_int = z_0[:, 3 + a:] * cfg.norm_values[2] + cfg.norm_biases[2]
+        d_int = h_integer - est_int
+        log_ph_int = torch.log(_cdf_std_gaussian((d_int + 0.5) / (sig0 * cfg.norm_values[2]))
+                               - _cdf_std_gaussian((d_int - 0.5) / (sig0 * cfg.norm_values[2])) + 1e-10)
+        log_ph_int = sum_mol(log_ph_int * mf[:, None])
+    else:
+        log_ph_int = torch.zeros(nmol)                                          # sum over an empty feature axis
+    loss_0_h = -(log_ph_int + log_ph_cat)
+    # log p(N) (models/__init__.py:264-308)
+    keys = list(n_nodes_hist.keys())
+    prob = torch.tensor([float(n_nodes_hist[k]) for k in keys])
+    prob = prob / prob.sum()
+    log_pn = torch.log(prob + 1e-30)[torch.tensor([keys.index(int(n)) for n in num_nodes.tolist()])]
+    # assembly, evaluation branch (qm9_mol_gen_ddpm.py:247-262)
+    loss_t = T * 0.5 * snr_weight * error_t
+    nll = loss_t + (loss_0_x + loss_0_h + neg_log_constants) + kl_prior - delta_log_px - log_pn
+    terms = dict(delta_log_px=delta_log_px, error_t=error_t, SNR_weight=snr_weight, loss_0_x=loss_0_x,
+                 loss_0_h=loss_0_h, neg_log_constants=neg_log_constants, kl_prior=kl_prior, log_pN=log_pn,
+                 t_int=t_int.squeeze(-1))
+    return nll, terms

@@ -105,6 +105,41 @@ def chain_case(cname, sizes, steps, seed, scale=0.5):
                 z_0=zs[-1], gamma=ddpm.gamma.gamma.data.clone())
 
 
+def nll_case(cname, sizes, seed, scale=0.5):
+    """Evaluation-mode NLL terms of the reference (EquivariantVariationalDiffusion.forward with .eval(), two denoiser
+    calls) + the Lightning module's evaluation assembly restated from qm9_mol_gen_ddpm.py:247-262."""
+    hist = {19: 5, 7: 2, 12: 3, 30: 1, 6: 1, 18: 2, 44: 3, 43: 2, 25: 1}
+    ddpm, _ = ref_shim.build_reference_ddpm(cname, seed=0, n_nodes_hist=hist)
+    cfg = O.config_named(cname)
+    sd = O.random_state_dict(cfg, WEIGHT_SEED, scale=scale)
+    ddpm.dynamics_network.load_state_dict(sd, strict=True)
+    ddpm.eval()
+    g = torch.Generator().manual_seed(seed)
+    nmol = len(sizes)
+    bi = torch.repeat_interleave(torch.arange(nmol), torch.tensor(sizes))
+    n = bi.shape[0]
+    mask = torch.ones(n, dtype=torch.bool)
+    mask[sizes[0] + 1] = False
+    x = torch.randn((n, 3), generator=g) * mask[:, None]
+    _, x = O.centralize(x, bi, mask, nmol)
+    types = torch.randint(0, cfg.num_atom_types, (n,), generator=g)
+    one_hot = torch.nn.functional.one_hot(types, cfg.num_atom_types).float() * mask[:, None]
+    charges = (torch.randint(1, 9, (n,), generator=g).float() * mask) if cfg.include_charges else torch.zeros((n, 0))
+    num_present = torch.zeros(nmol, dtype=torch.long).index_add_(0, bi, mask.long())
+    batch = ref_shim.Batch(batch=bi, mask=mask, x=x.clone(), h={"categorical": one_hot.clone(), "integer": charges.clone()},
+                           num_graphs=nmol, num_nodes_present=num_present, props_context=None)
+    torch.manual_seed(seed + 1000)
+    with torch.no_grad():
+        (dlp, err, snr, l0x, l0h, nlc, klp, lpn, tint, _info) = ddpm(batch, return_loss_info=True)
+    T = cfg.num_timesteps
+    nll = T * 0.5 * snr * err + (l0x + l0h + nlc) + klp - dlp - lpn
+    return dict(config=cname, sizes=list(sizes), weight_seed=WEIGHT_SEED, weight_scale=scale,
+                weight_checksum=weight_checksum(sd), histogram=hist, rng_seed=seed + 1000, batch_index=bi, mask=mask, x=x,
+                one_hot=one_hot, charges=charges, nll=nll.clone(),
+                terms=dict(delta_log_px=dlp, error_t=err, SNR_weight=snr, loss_0_x=l0x, loss_0_h=l0h,
+                           neg_log_constants=nlc, kl_prior=klp, log_pN=lpn, t_int=tint))
+
+
 def main():
     fixtures = {
         # SURVEY.md §8c (i): integer KAT for the edge index, observed from the reference
@@ -118,6 +153,8 @@ def main():
         "chain_qm9_T6": chain_case("qm9", [19, 7, 12], 6, 123),
         "chain_qm9_cond_T4": chain_case("qm9_cond", [9, 14], 4, 321),
         "chain_geom_T3": chain_case("geom", [30, 44], 3, 77),
+        "nll_qm9": nll_case("qm9", [19, 7, 12], 5),
+        "nll_geom": nll_case("geom", [30, 44, 25], 6),
     }
     from src.models.components.gcpnet import GCPNetDynamics
     bi = torch.tensor([0] * 5 + [1] * 5)

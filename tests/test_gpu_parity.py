@@ -213,3 +213,23 @@ def test_full_size_properties_qm9_b128():
     ref = O.denoiser_forward(sd, ocfg, bi[sl].cpu(), mask[sl].cpu(), xh[sl].cpu(), t[sl].cpu())
     # all rows except the last atom of the slice see the same neighbours as in the full batch
     assert relerr(out[sl][:3 * nat].cpu(), ref[:3 * nat]) <= 5e-5
+
+
+@pytest.mark.parametrize("name", ["nll_qm9", "nll_geom"])
+def test_eval_nll_on_device_matches_reference(name):
+    """GCDMEvalNLL (two denoiser calls through the C ABI + torch bookkeeping on the GPU) vs the reference's terms.
+    The CPU noise stream of the fixture is replayed; tolerance 1e-4 relative on every term and on the NLL."""
+    import bdiff
+    fx = load_golden(name)
+    net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], scale=fx["weight_scale"])
+    ev = bdiff.GCDMEvalNLL(net, fx["histogram"])
+    torch.manual_seed(fx["rng_seed"])
+    t_int = torch.randint(1, ocfg.num_timesteps + 1, size=(len(fx["sizes"]), 1))      # same first draw as the reference
+    assert torch.equal(t_int.squeeze(-1), fx["terms"]["t_int"])
+    nll, terms = ev(fx["batch_index"].cuda(), fx["mask"].cuda(), fx["x"].cuda(), fx["one_hot"].cuda(),
+                    fx["charges"].cuda(), None, t_int=t_int, noise=lambda s: torch.randn(s))
+    for k, ref in fx["terms"].items():
+        if k == "t_int":
+            continue
+        assert torch.allclose(terms[k].cpu(), ref, rtol=1e-4, atol=1e-4), (k, terms[k].cpu(), ref)
+    assert torch.allclose(nll.cpu(), fx["nll"], rtol=1e-4, atol=1e-3)

@@ -95,3 +95,19 @@ def test_se3_equivariance_of_oracle():
     o2 = O.denoiser_forward(sd, cfg, bi, mask, torch.cat((xc @ Q.T, xh[:, 3:]), -1), t, dtype=torch.float64)
     assert (o2[:, :3] - o1[:, :3] @ Q.double().T).abs().max() < 1e-6
     assert (o2[:, 3:] - o1[:, 3:]).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["nll_qm9", "nll_geom"])
+def test_eval_nll_matches_reference(name):
+    """Evaluation-mode NLL terms (two denoiser calls) vs the reference; same global RNG stream."""
+    fx = load_golden(name)
+    cfg, sd = weights_for(fx)
+    torch.manual_seed(fx["rng_seed"])
+    nll, terms = O.eval_nll(sd, cfg, fx["batch_index"], fx["mask"], fx["x"], fx["one_hot"], fx["charges"], None,
+                            fx["histogram"], lambda s: torch.randn(s))
+    assert torch.equal(terms["t_int"], fx["terms"]["t_int"])
+    for k, ref in fx["terms"].items():
+        if k == "t_int":
+            continue
+        assert torch.allclose(terms[k], ref, rtol=1e-5, atol=1e-5), k
+    assert torch.allclose(nll, fx["nll"], rtol=1e-5, atol=1e-4)
