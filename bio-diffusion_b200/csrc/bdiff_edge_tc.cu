@@ -223,9 +223,12 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
                                             const float* __restrict__ Wu, const float* __restrict__ bgp,
                                             const float* __restrict__ Wdn, const float* __restrict__ Wfn,
                                             float* __restrict__ part) {   // part[33]: partial VD_next(24)+VDF_next(9)
+  float2 p2[4][3];                 // VD_next accumulators, pairs of hidden rows (h = 2hp, 2hp+1) per component
   if (!LAST) {
 #pragma unroll
     for (int i = 0; i < 33; ++i) part[i] = 0.f;
+#pragma unroll
+    for (int hp = 0; hp < 4; ++hp) { p2[hp][0] = make_float2(0.f, 0.f); p2[hp][1] = p2[hp][0]; p2[hp][2] = p2[hp][0]; }
   }
   for (int oc = half * 2; oc < half * 2 + 2; ++oc) {
     float u[8], mv[24];
@@ -246,19 +249,27 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int o = oc * 8 + j;
-      const float g = sigmoid_fast(u[j] + bgp[o]);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (int jp = 0; jp < 4; ++jp) {          // two output channels (j = 2jp, 2jp+1) per packed instruction
+      const int o = oc * 8 + 2 * jp;
+      const float2 g = sigmoid_fast2(__fadd2_rn(make_float2(u[2 * jp], u[2 * jp + 1]),
+                                                *reinterpret_cast<const float2*>(bgp + o)));
+      float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0;
 #pragma unroll
       for (int h = 0; h < HP; ++h) {
-        const float wu = Wu[h * 32 + o];
-        s0 = fmaf(wu, vdp[h * 3 + 0], s0);
-        s1 = fmaf(wu, vdp[h * 3 + 1], s1);
-        s2 = fmaf(wu, vdp[h * 3 + 2], s2);
+        const float2 wu = *reinterpret_cast<const float2*>(Wu + h * 32 + o);
+        s0 = __ffma2_rn(wu, make_float2(vdp[h * 3 + 0], vdp[h * 3 + 0]), s0);
+        s1 = __ffma2_rn(wu, make_float2(vdp[h * 3 + 1], vdp[h * 3 + 1]), s1);
+        s2 = __ffma2_rn(wu, make_float2(vdp[h * 3 + 2], vdp[h * 3 + 2]), s2);
       }
-      if (FIRST) { mv[j * 3] = s0 * g; mv[j * 3 + 1] = s1 * g; mv[j * 3 + 2] = s2 * g; }
-      else { mv[j * 3] = fmaf(s0, g, mv[j * 3]); mv[j * 3 + 1] = fmaf(s1, g, mv[j * 3 + 1]); mv[j * 3 + 2] = fmaf(s2, g, mv[j * 3 + 2]); }
+      const int ja = 2 * jp * 3, jb = (2 * jp + 1) * 3;
+      float2 r0, r1, r2;
+      if (FIRST) { r0 = __fmul2_rn(s0, g); r1 = __fmul2_rn(s1, g); r2 = __fmul2_rn(s2, g); }
+      else {
+        r0 = __ffma2_rn(s0, g, make_float2(mv[ja + 0], mv[jb + 0]));
+        r1 = __ffma2_rn(s1, g, make_float2(mv[ja + 1], mv[jb + 1]));
+        r2 = __ffma2_rn(s2, g, make_float2(mv[ja + 2], mv[jb + 2]));
+      }
+      mv[ja + 0] = r0.x; mv[jb + 0] = r0.y; mv[ja + 1] = r1.x; mv[jb + 1] = r1.y; mv[ja + 2] = r2.x; mv[jb + 2] = r2.y;
     }
     tmem_st8xN<3>(tl + TM_MV + oc * 24, mv);      // completion awaited once, at the end of the function
     if (!LAST) {
@@ -266,12 +277,13 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
       for (int j = 0; j < 8; ++j) {
         const int c = oc * 8 + j;
         const float4 wd0 = *reinterpret_cast<const float4*>(Wdn + c * 8), wd1 = *reinterpret_cast<const float4*>(Wdn + c * 8 + 4);
-        const float wd[8] = {wd0.x, wd0.y, wd0.z, wd0.w, wd1.x, wd1.y, wd1.z, wd1.w};
+        const float2 wdp[4] = {make_float2(wd0.x, wd0.y), make_float2(wd0.z, wd0.w), make_float2(wd1.x, wd1.y),
+                               make_float2(wd1.z, wd1.w)};
 #pragma unroll
-        for (int h = 0; h < 8; ++h) {
-          part[h * 3 + 0] = fmaf(wd[h], mv[j * 3 + 0], part[h * 3 + 0]);
-          part[h * 3 + 1] = fmaf(wd[h], mv[j * 3 + 1], part[h * 3 + 1]);
-          part[h * 3 + 2] = fmaf(wd[h], mv[j * 3 + 2], part[h * 3 + 2]);
+        for (int x = 0; x < 3; ++x) {
+          const float2 mb = make_float2(mv[j * 3 + x], mv[j * 3 + x]);
+#pragma unroll
+          for (int hp = 0; hp < 4; ++hp) p2[hp][x] = __ffma2_rn(wdp[hp], mb, p2[hp][x]);
         }
 #pragma unroll
         for (int ch = 0; ch < 3; ++ch) {
@@ -282,6 +294,12 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
         }
       }
     }
+  }
+  if (!LAST) {
+#pragma unroll
+    for (int hp = 0; hp < 4; ++hp)
+#pragma unroll
+      for (int x = 0; x < 3; ++x) { part[(2 * hp) * 3 + x] = p2[hp][x].x; part[(2 * hp + 1) * 3 + x] = p2[hp][x].y; }
   }
   tmem_st_wait();
 }
@@ -533,10 +551,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
             a = *reinterpret_cast<const float4*>(pi + c0 + q * 4);
             bq = *reinterpret_cast<const float4*>(pj + c0 + q * 4);
           }
-          v[q * 4 + 0] = silu_fast(v[q * 4 + 0] + a.x + bq.x);
-          v[q * 4 + 1] = silu_fast(v[q * 4 + 1] + a.y + bq.y);
-          v[q * 4 + 2] = silu_fast(v[q * 4 + 2] + a.z + bq.z);
-          v[q * 4 + 3] = silu_fast(v[q * 4 + 3] + a.w + bq.w);
+          const float2 p0 = silu_fast2(__fadd2_rn(__fadd2_rn(make_float2(v[q * 4 + 0], v[q * 4 + 1]), make_float2(a.x, a.y)),
+                                                  make_float2(bq.x, bq.y)));
+          const float2 p1 = silu_fast2(__fadd2_rn(__fadd2_rn(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(a.z, a.w)),
+                                                  make_float2(bq.z, bq.w)));
+          v[q * 4 + 0] = p0.x; v[q * 4 + 1] = p0.y; v[q * 4 + 2] = p1.x; v[q * 4 + 3] = p1.y;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
@@ -544,7 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
       publish();
 
       float vd[24], vdf[9];
-      float adot = 0.f;
+      float2 adot2 = make_float2(0.f, 0.f);
       for (int k = 1; k <= 3; ++k) {
         // ---- E(k)a: gate_{k-1}, m.v update (this half's 16 channels), vector_down of GCP k -> A block 4
         wait_d();
@@ -602,20 +621,27 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
             x_load8(X, r, c0 + q * 8, m);
             const float4 b0 = *reinterpret_cast<const float4*>(&sw.bk[k - 1][c0 + q * 8]);
             const float4 b1 = *reinterpret_cast<const float4*>(&sw.bk[k - 1][c0 + q * 8 + 4]);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+            float2 mm[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] += silu_fast(v[q * 8 + i] + bb[i]);
+            for (int i = 0; i < 4; ++i)
+              mm[i] = __fadd2_rn(make_float2(m[2 * i], m[2 * i + 1]),
+                                 silu_fast2(__fadd2_rn(make_float2(v[q * 8 + 2 * i], v[q * 8 + 2 * i + 1]), bb[i])));
             if (k == 3) {
               const float4 w0 = *reinterpret_cast<const float4*>(&sw.wa[c0 + q * 8]);
               const float4 w1 = *reinterpret_cast<const float4*>(&sw.wa[c0 + q * 8 + 4]);
-              adot = fmaf(m[0], w0.x, adot); adot = fmaf(m[1], w0.y, adot); adot = fmaf(m[2], w0.z, adot);
-              adot = fmaf(m[3], w0.w, adot); adot = fmaf(m[4], w1.x, adot); adot = fmaf(m[5], w1.y, adot);
-              adot = fmaf(m[6], w1.z, adot); adot = fmaf(m[7], w1.w, adot);
+              adot2 = __ffma2_rn(mm[0], make_float2(w0.x, w0.y), adot2);
+              adot2 = __ffma2_rn(mm[1], make_float2(w0.z, w0.w), adot2);
+              adot2 = __ffma2_rn(mm[2], make_float2(w1.x, w1.y), adot2);
+              adot2 = __ffma2_rn(mm[3], make_float2(w1.z, w1.w), adot2);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { m[2 * i] = mm[i].x; m[2 * i + 1] = mm[i].y; }
             x_store8(X, r, c0 + q * 8, m);
           }
         }
-        if (k == 3) T.sAttn[half][r] = adot;
+        if (k == 3) T.sAttn[half][r] = adot2.x + adot2.y;
         publish();
       }
       // ---- E4: gate_3 and the last m.v update

@@ -171,6 +171,14 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 __device__ __forceinline__ float silu_fast(float x) { return x * sigmoid_fast(x); }
 
+// packed fp32x2 versions (FFMA2 / FMUL2 / FADD2 on sm_100a: two lanes per issued instruction)
+__device__ __forceinline__ float2 sigmoid_fast2(float2 x) {
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  const float2 t = make_float2(tanh_fast(hx.x), tanh_fast(hx.y));
+  return __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+}
+__device__ __forceinline__ float2 silu_fast2(float2 x) { return __fmul2_rn(x, sigmoid_fast2(x)); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
