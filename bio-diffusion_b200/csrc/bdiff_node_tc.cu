@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
                      i32n = umma_idesc_bf16(32, true);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0;
-      int ms = 32;
+      int ms = 28;
       auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); BDIFF_STAMP(ms++); };
       auto wait_w = [&]() -> uint32_t {
         const uint32_t s = ci % NSTAGES;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const SmallWN& sw = T.sw;
     uint32_t pd = 0;
-    int es = 0;
+    int es = 0, fs = 52;
     auto wait_d = [&]() { if (tid == 0) BDIFF_STAMP(es++); mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); if (tid == 0) BDIFF_STAMP(es++); };
     auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); if (tid == 0) BDIFF_STAMP(es++); };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         f[8] = w.fbar[(size_t)node * 12 + 8];
       }
       // ---- T0: agg_s -> A blocks 0..3 (coalesced); vector_down (this half's 8 rows) / vector_down_frames of the FF GCP
+      if (tid == 0) BDIFF_STAMP(fs++);
       stage_rows(X, w.agg + (size_t)tile * NTM * kMsg + half * 128, kMsg, half * 128, wih, lane);
+      if (tid == 0) BDIFF_STAMP(fs++);
       {
         float vdh[24], vdf[9];
 #pragma unroll
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
             }
           }
         }
+        if (tid == 0) BDIFF_STAMP(fs++);
 #pragma unroll
         for (int h = 0; h < 8; ++h)
           x_store1(X, r, 256 + half * 8 + h, safe_norm3(vdh[h * 3], vdh[h * 3 + 1], vdh[h * 3 + 2]));
@@ -344,7 +347,9 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
           }
           tmem_st8xN<6>(tl + NM_CHI + half * 48, cown);
         }
+        if (tid == 0) BDIFF_STAMP(fs++);
         tmem_st_wait();
+        if (tid == 0) BDIFF_STAMP(fs++);
       }
       publish();
       // ---- T0b: h -> A blocks 0..3 (after G1a has consumed agg_s)

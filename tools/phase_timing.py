@@ -31,8 +31,9 @@ st = raw.contiguous().view(torch.int64).reshape(256, 64).cpu()
 # the node kernel ran last (19 CTAs); the edge kernel's stamps survive in CTAs >= 19
 rows = range(0, 4) if which == "node" else range(40, 44)
 for c in rows:
-    e = st[c, :32].tolist()
-    m = st[c, 32:].tolist()
+    fine = [v for v in st[c, 52:64].tolist() if v > 0]
+    e = st[c, :28].tolist()
+    m = st[c, 28:52].tolist()
     e = [v for v in e if v > 0]
     m = [v for v in m if v > 0]
     if not e:
@@ -40,5 +41,7 @@ for c in rows:
     t0 = e[0]
     print(f"CTA {c}: epilogue stamps (cycles since tile start):", [v - t0 for v in e])
     print(f"        deltas:", [e[i + 1] - e[i] for i in range(len(e) - 1)])
+    if fine:
+        print(f"        fine stamps (T0 sub-phases):", [v - t0 for v in fine])
     if m:
         print(f"        MMA-thread stamps:", [v - t0 for v in m])
