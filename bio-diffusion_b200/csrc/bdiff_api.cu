@@ -57,7 +57,7 @@ struct bdiff_handle {
   // plan
   bool have_plan = false;
   Plan plan{};
-  DevBuf plan_buf;
+  DevBuf plan_buf, rc_buf;
   int Npad = 0;
   long long Epad = 0;
 
@@ -352,7 +352,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
 void bdiff_destroy(bdiff_handle* h) {
   if (!h) return;
   if (h->wbuf) cudaFree(h->wbuf);
-  h->plan_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
+  h->plan_buf.release(); h->rc_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
   delete h;
 }
 
@@ -493,6 +493,16 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   p.edge_off = reinterpret_cast<long long*>(base + o_eo);
   p.tile_mol = reinterpret_cast<int*>(base + o_tm);
   p.mask = base + o_mk;
+  p.edge_rc = nullptr;
+  {
+    const long long nrc = ntile128 * 128;
+    e = h->rc_buf.ensure((size_t)(nrc > 0 ? nrc : 1) * sizeof(int4));
+    if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "plan edge records: %s", cudaGetErrorString(e));
+    launch_edge_rc(st, p, static_cast<int4*>(h->rc_buf.p), nrc);
+    p.edge_rc = static_cast<const int4*>(h->rc_buf.p);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "plan edge records: %s", cudaGetErrorString(e));
+  }
   h->Npad = round_up(N, 128);
   h->Epad = (E + 127) / 128 * 128 + 128;
   e = ensure_work(h);

@@ -35,6 +35,7 @@ struct Plan {
   const int* node_mol;   // [N]   molecule of each node
   const int* tile_mol;   // [ceil(E/128)] molecule that contains edge 128*t (start of the linear molecule search)
   const unsigned char* mask;  // [N]
+  const int4* edge_rc;   // [128*ceil(E/128)] per edge {row, col, b, nact} (row = -1 past E): b = position in the row segment
 };
 
 // Per-layer packed weights (device pointers, K-major).

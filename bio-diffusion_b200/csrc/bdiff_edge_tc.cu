@@ -204,8 +204,10 @@ struct alignas(16) SmallW {   // fp32 copies of the thread-local (vector channel
   float ba[4];
 };
 
+constexpr int ST_LD = 37;
 struct TcSmemTail {
-  float sT[2][TMT][33];    // per-half transpose buffer of the final reduction; reused as the pair-exchange buffer
+  float sT[2][TMT][ST_LD]; // per-half transpose buffer of the final reduction; reused as the pair-exchange buffer and as
+                           // the staging area of the coalesced xi / P_j gathers
   SmallW sw;
   float sAttn[2][TMT];
   int sRow[TMT], sCol[TMT], sB[TMT], sNa[TMT];
@@ -455,48 +457,94 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       if (tid == 0) BDIFF_STAMP(es++);
       const long long g = (long long)tile * TMT + r;
-      int row = -1, col = -1, b = 0, na = 0;
-      if (g < p.E) {
-        const int k = find_mol_from(p.edge_off, __ldg(p.tile_mol + tile), g);
-        const int loc = (int)(g - p.edge_off[k]);
-        const int a0 = p.act_off[k];
-        na = p.act_off[k + 1] - a0;
-        const int a = loc / na;
-        b = loc - a * na;
-        row = p.act_idx[a0 + a];
-        col = p.act_idx[a0 + b];
-      }
-      if (half == 0) { T.sRow[r] = row; T.sCol[r] = col; T.sB[r] = b; T.sNa[r] = na; }
+      // ---- T0: A operand of GCP 0 = [e | vn0 | q0]; VD0 goes to TMEM scratch for the vector_up of GCP 0.
+      // Global reads are issued so that (a) one warp instruction touches a few 128-byte lines (the L1 handles one
+      // line tag per cycle, so "lane = edge row" gathers cost 32 cycles each) and (b) independent loads are in
+      // flight together: the per-edge record, e, xi and the frames first; then, once (row, col) are known, the
+      // endpoint vector parts.  e and xi are contiguous per tile and are staged by all threads in row-major order;
+      // P_j rows are gathered 8..18 lanes per row through shared memory.
+      float* sF = &T.sT[0][0][0];
+      constexpr int PV = HID0 * 3 + 9, PF4 = (PV + 3) / 4, PLD = PF4 * 4 + 1;
+      constexpr int XF4 = XD * 3 / 4, XLD = XD * 3 + 1;
+      static_assert(TMT * PLD <= 2 * TMT * ST_LD && TMT * XLD <= 2 * TMT * ST_LD, "staging area");
+      const int4 rc = __ldg(p.edge_rc + g);
       float f[9];
-#pragma unroll
-      for (int q = 0; q < 9; ++q) f[q] = w.frames[(size_t)g * 9 + q];
-      const float* pi = w.PI + (size_t)(row < 0 ? 0 : row) * kPStride;
-      const float* pj = w.PJ + (size_t)(col < 0 ? 0 : col) * kPStride;
-
-      // ---- T0: A operand of GCP 0 = [e | vn0 | q0]; VD0 goes to TMEM scratch for the vector_up of GCP 0
       {
-        // this half's share of e (ED/2 columns)
-        const float* er = w.e + (size_t)g * ED + half * (ED / 2);
+        constexpr int F4_ROW = ED / 4;
+        const float4* eb = reinterpret_cast<const float4*>(w.e + (size_t)tile * TMT * ED);
+        const float4* xb = reinterpret_cast<const float4*>(w.xi + (size_t)tile * TMT * XD * 3);
+        float4 ev[TMT * F4_ROW / TC_EPI], xv[TMT * XF4 / TC_EPI];
 #pragma unroll
-        for (int c8 = 0; c8 < ED / 2; c8 += 8) {
-          const float4 a = *reinterpret_cast<const float4*>(er + c8), bq = *reinterpret_cast<const float4*>(er + c8 + 4);
-          const float v[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-          x_store8(X, r, half * (ED / 2) + c8, v);
-        }
-        float xi[XD * 3];
-        const float* xr = w.xi + (size_t)g * (XD * 3);
+        for (int i = 0; i < TMT * F4_ROW / TC_EPI; ++i) ev[i] = eb[i * TC_EPI + tid];
 #pragma unroll
-        for (int c4 = 0; c4 < XD * 3; c4 += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(xr + c4);
-          xi[c4] = a.x; xi[c4 + 1] = a.y; xi[c4 + 2] = a.z; xi[c4 + 3] = a.w;
+        for (int i = 0; i < TMT * XF4 / TC_EPI; ++i) xv[i] = xb[i * TC_EPI + tid];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) f[q] = w.frames[(size_t)g * 9 + q];
+        if (half == 0) { T.sRow[r] = rc.x; T.sCol[r] = rc.y; T.sB[r] = rc.z; T.sNa[r] = rc.w; }
+#pragma unroll
+        for (int i = 0; i < TMT * F4_ROW / TC_EPI; ++i) {
+          const int idx = i * TC_EPI + tid;
+          const int rr = idx / F4_ROW, kk = (idx % F4_ROW) * 4;
+          *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(rr, kk & 63)) =
+              make_uint2(pack_bf16x2(ev[i].x, ev[i].y), pack_bf16x2(ev[i].z, ev[i].w));
         }
-        // vector_down rows [half*H2, half*H2 + H2) of GCP 0 (split form: endpoint parts gathered)
-        float vdh[32];
+#pragma unroll
+        for (int i = 0; i < TMT * XF4 / TC_EPI; ++i) {
+          const int idx = i * TC_EPI + tid;
+          float* dst = sF + (idx / XF4) * XLD + (idx % XF4) * 4;
+          dst[0] = xv[i].x; dst[1] = xv[i].y; dst[2] = xv[i].z; dst[3] = xv[i].w;
+        }
+      }
+      const int row = rc.x;
+      const float* pi = w.PI + (size_t)(row < 0 ? 0 : row) * kPStride;
+      named_bar_sync(3, TC_EPI);           // xi staged; sRow / sCol visible
+      {
+        // vector parts of P_j (vector_down + vector_down_frames contributions of the target node): gather
+        float4 pv[(TMT * PF4 + TC_EPI - 1) / TC_EPI];
+#pragma unroll
+        for (int i = 0; i < (TMT * PF4 + TC_EPI - 1) / TC_EPI; ++i) {
+          const int idx = i * TC_EPI + tid;
+          pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < TMT * PF4) {
+            const int rr = idx / PF4, cj = T.sCol[rr];
+            if (cj >= 0) pv[i] = *reinterpret_cast<const float4*>(w.PJ + (size_t)cj * kPStride + kH + (idx - rr * PF4) * 4);
+          }
+        }
+        // ... and of P_i (rows shared by consecutive edges -> broadcast loads), in flight at the same time
+        float vdh[32], vdf0[9];
 #pragma unroll
         for (int i = 0; i < 32; ++i) vdh[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) vdf0[i] = 0.f;
         if (row >= 0) {
 #pragma unroll
-          for (int i = 0; i < H2 * 3; ++i) vdh[i] = pi[kH + half * H2 * 3 + i] + pj[kH + half * H2 * 3 + i];
+          for (int i = 0; i < H2 * 3; ++i) vdh[i] = pi[kH + half * H2 * 3 + i];
+          if (half == 0) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) vdf0[i] = pi[kH + HID0 * 3 + i];
+          }
+        }
+        float xi[XD * 3];
+#pragma unroll
+        for (int c = 0; c < XD * 3; ++c) xi[c] = sF[r * XLD + c];
+        named_bar_sync(3, TC_EPI);         // everybody has read xi
+#pragma unroll
+        for (int i = 0; i < (TMT * PF4 + TC_EPI - 1) / TC_EPI; ++i) {
+          const int idx = i * TC_EPI + tid;
+          if (idx < TMT * PF4) {
+            const int rr = idx / PF4;
+            float* dst = sF + rr * PLD + (idx - rr * PF4) * 4;
+            dst[0] = pv[i].x; dst[1] = pv[i].y; dst[2] = pv[i].z; dst[3] = pv[i].w;
+          }
+        }
+        named_bar_sync(3, TC_EPI);
+        const float* pjv = sF + r * PLD;
+        // vector_down rows [half*H2, half*H2 + H2) of GCP 0 (split form: endpoint parts gathered)
+#pragma unroll
+        for (int i = 0; i < H2 * 3; ++i) vdh[i] += pjv[half * H2 * 3 + i];
+        if (half == 0) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) vdf0[i] += pjv[HID0 * 3 + i];
         }
 #pragma unroll
         for (int c = 0; c < XD; ++c) {
@@ -515,9 +563,6 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
         tmem_st_wait();
         if (half == 0) {
           // vector_down_frames of GCP 0 and its scalarisation q0 (9 values), plus the zero padding
-          float vdf0[9];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) vdf0[i] = row >= 0 ? pi[kH + HID0 * 3 + i] + pj[kH + HID0 * 3 + i] : 0.f;
 #pragma unroll
           for (int c = 0; c < XD; ++c)
 #pragma unroll
@@ -539,26 +584,55 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
       }
       publish();
 
-      // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col]), this half's 128 columns
-      wait_d();
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 64) {
-        float v[64];
-        tmem_ld64(tl + TM_S + c0, v);
+      // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col]), this half's 128 columns in 4 rounds of 32.  P_i rows are
+      //      shared by consecutive edges (broadcast loads); P_j rows are gathered 8 lanes per row into sT[half].
+      //      The loads of round c+1 are in flight while round c is computed.
+      {
+        float4 buf[8], pa[8];
+        auto prefetch = [&](int c) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
-          if (row >= 0) {
-            a = *reinterpret_cast<const float4*>(pi + c0 + q * 4);
-            bq = *reinterpret_cast<const float4*>(pj + c0 + q * 4);
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * TC_EPI + tid;
+            const int hh = idx >> 10, rr = (idx >> 3) & 127, c4 = idx & 7;
+            const int cj = T.sCol[rr];
+            buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cj >= 0) buf[i] = *reinterpret_cast<const float4*>(w.PJ + (size_t)cj * kPStride + hh * 128 + c * 32 + c4 * 4);
           }
-          const float2 p0 = silu_fast2(__fadd2_rn(__fadd2_rn(make_float2(v[q * 4 + 0], v[q * 4 + 1]), make_float2(a.x, a.y)),
-                                                  make_float2(bq.x, bq.y)));
-          const float2 p1 = silu_fast2(__fadd2_rn(__fadd2_rn(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(a.z, a.w)),
-                                                  make_float2(bq.z, bq.w)));
-          v[q * 4 + 0] = p0.x; v[q * 4 + 1] = p0.y; v[q * 4 + 2] = p1.x; v[q * 4 + 3] = p1.y;
-        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
+          for (int q = 0; q < 8; ++q) {
+            pa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row >= 0) pa[q] = *reinterpret_cast<const float4*>(pi + half * 128 + c * 32 + q * 4);
+          }
+        };
+        prefetch(0);
+        wait_d();
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int idx = i * TC_EPI + tid;
+            float* dst = &T.sT[idx >> 10][(idx >> 3) & 127][(idx & 7) * 4];
+            dst[0] = buf[i].x; dst[1] = buf[i].y; dst[2] = buf[i].z; dst[3] = buf[i].w;
+          }
+          const int c0 = half * 128 + c * 32;
+          float v[32];
+          tmem_ld32(tl + TM_S + c0, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[q * 4 + 0] += pa[q].x; v[q * 4 + 1] += pa[q].y; v[q * 4 + 2] += pa[q].z; v[q * 4 + 3] += pa[q].w;
+          }
+          named_bar_sync(3, TC_EPI);
+          if (c < 3) prefetch(c + 1);
+          const float* pjs = &T.sT[half][r][0];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 p0 = silu_fast2(__fadd2_rn(make_float2(v[q * 4 + 0], v[q * 4 + 1]), make_float2(pjs[q * 4 + 0], pjs[q * 4 + 1])));
+            const float2 p1 = silu_fast2(__fadd2_rn(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(pjs[q * 4 + 2], pjs[q * 4 + 3])));
+            v[q * 4 + 0] = p0.x; v[q * 4 + 1] = p0.y; v[q * 4 + 2] = p1.x; v[q * 4 + 3] = p1.y;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
+          named_bar_sync(3, TC_EPI);
+        }
       }
       publish();
 

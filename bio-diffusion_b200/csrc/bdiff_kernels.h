@@ -48,6 +48,7 @@ void launch_step(cudaStream_t st, const Plan& p, const Dims& d, int mode, const 
                  const float* noise_x, const float* noise_h, const float* coef_table, const int* step_ptr,
                  float* out);
 void launch_edge_index(cudaStream_t st, const Plan& p, long long* out);
+void launch_edge_rc(cudaStream_t st, const Plan& p, int4* out, long long n);
 void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
                  int kpad, int nout);
 

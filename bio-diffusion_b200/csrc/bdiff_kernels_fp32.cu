@@ -864,6 +864,22 @@ __global__ void k_edge_index(Plan p, long long* __restrict__ out) {
   out[p.E + g] = p.act_idx[a0 + b];
 }
 
+// Per-edge record used by the tensor-core edge pass: one coalesced 16-byte load instead of a chain of dependent
+// lookups (edge_off -> act_off -> act_idx) at the top of every tile.
+__global__ void k_edge_rc(Plan p, int4* __restrict__ out, long long n) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  int4 v = make_int4(-1, -1, 0, 0);
+  if (g < p.E) {
+    const int k = find_mol(p.edge_off, p.B, g);
+    const int loc = (int)(g - p.edge_off[k]);
+    const int a0 = p.act_off[k], na = p.act_off[k + 1] - a0;
+    const int a = loc / na, b = loc - a * na;
+    v = make_int4(p.act_idx[a0 + a], p.act_idx[a0 + b], b, na);
+  }
+  out[g] = v;
+}
+
 // dst[k*dst_ld + o] = k < ncols ? src[o*src_ld + col0 + k] : 0   (torch [out,in] weight -> K-major, padded)
 __global__ void k_pack(float* __restrict__ dst, int dst_ld, const float* __restrict__ src, int src_ld, int col0,
                        int ncols, int kpad, int nout) {
@@ -922,6 +938,9 @@ void launch_step(cudaStream_t st, const Plan& p, const Dims& d, int mode, const 
 }
 void launch_edge_index(cudaStream_t st, const Plan& p, long long* out) {
   if (p.E > 0) k_edge_index<<<(unsigned)((p.E + 255) / 256), 256, 0, st>>>(p, out);
+}
+void launch_edge_rc(cudaStream_t st, const Plan& p, int4* out, long long n) {
+  if (n > 0) k_edge_rc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, out, n);
 }
 void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
                  int kpad, int nout) {

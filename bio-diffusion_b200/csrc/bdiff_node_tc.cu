@@ -655,7 +655,8 @@ void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, co
 void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms) {
   // small batches (one wave of 32-node tiles): the row-replicated kernel; BDIFF_NODE_R4=0/1 overrides
-  static const int force = [] { const char* e = getenv("BDIFF_NODE_R4"); return e ? atoi(e) : -1; }();
+  const char* env = getenv("BDIFF_NODE_R4");      // read per launch so that tests can exercise both kernels
+  const int force = env ? atoi(env) : -1;
   const int nt32 = (p.N + 31) / 32;
   if (force == 1 || (force < 0 && nt32 <= num_sms)) {
     const int grid = nt32 < num_sms ? nt32 : num_sms;

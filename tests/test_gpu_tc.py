@@ -43,9 +43,11 @@ def make_net(cname, seed, mode, scale=1.0):
     return net.cuda(), ocfg, sd
 
 
+@pytest.mark.parametrize("node_r4", ["0", "1"])     # 128-node-tile kernel / row-replicated 32-node-tile kernel
 @pytest.mark.parametrize("name", ["qm9_small_masked", "qm9_tiny_sizes", "qm9_b4_n19", "qm9_cond", "geom_mixed",
                                   "geom_max181"])
-def test_tensor_forward_close_to_reference(name):
+def test_tensor_forward_close_to_reference(name, node_r4, monkeypatch):
+    monkeypatch.setenv("BDIFF_NODE_R4", node_r4)
     fx = load_golden(name)
     net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], "tensor")
     ctx = fx["context"].cuda() if fx["context"] is not None else None
@@ -59,10 +61,16 @@ def test_tensor_forward_close_to_reference(name):
     assert max_abs <= 2e-2 * scale and rms <= 5e-3 * scale
 
 
-def test_tensor_and_parity_modes_agree_full_size():
-    """QM9 B=128: tensor mode vs parity mode on the same input (both on the GPU)."""
+@pytest.mark.parametrize("b,node_r4", [(128, None), (128, "0"), (300, "1"), (300, None)])
+def test_tensor_and_parity_modes_agree_full_size(b, node_r4, monkeypatch):
+    """QM9 B=128 (BASELINE config) and B=300 (more 32-node tiles than SMs: persistent loop of the row-replicated node
+    kernel when forced, 128-node tiles by default): tensor mode vs parity mode on the same input, both on the GPU."""
+    if node_r4 is not None:
+        monkeypatch.setenv("BDIFF_NODE_R4", node_r4)
+    else:
+        monkeypatch.delenv("BDIFF_NODE_R4", raising=False)
     g = torch.Generator().manual_seed(4)
-    b, nat = 128, 19
+    nat = 19
     n = b * nat
     bi = torch.repeat_interleave(torch.arange(b), torch.full((b,), nat)).cuda()
     mask = torch.ones(n, dtype=torch.bool, device="cuda")

@@ -28,8 +28,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 raw = net.debug_tap("dbg")                      # [256, 128] float32 view of [256][64] int64
 st = raw.contiguous().view(torch.int64).reshape(256, 64).cpu()
-# the node kernel ran last (19 CTAs); the edge kernel's stamps survive in CTAs >= 19
-rows = range(0, 4) if which == "node" else range(40, 44)
+# the node kernel ran last (<= 76 CTAs at this size); the edge kernel stamps survive in CTAs above that
+rows = range(0, 4) if which == "node" else range(100, 104)
 for c in rows:
     fine = [v for v in st[c, 52:64].tolist() if v > 0]
     e = st[c, :28].tolist()
