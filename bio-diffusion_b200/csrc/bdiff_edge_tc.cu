@@ -728,61 +728,61 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
       named_bar_sync(3, TC_EPI);     // m.v of both halves in TMEM, sAttn/sRow/... visible
       tc_fence_after();
       const float attn = sigmoid_fast(T.sAttn[0][r] + T.sAttn[1][r] + sw.ba[0]);
-      // ---- segmented sum over the source node.  Chunks of 32 message columns: 0..7 = m.s, 8..10 = m.v.
-      // half 0 reduces chunks {0,1,2,3,8}, half 1 {4,5,6,7,9,10}; each half has its own transpose buffer.
-      // Reducer mapping: warp handles the 32 rows q0..q0+31, lane = column.  Segment structure of those rows
-      // as warp-uniform bit masks (bit i <-> row q0+i).
-      const int q0 = (r >> 5) * 32;
-      uint32_t m_valid, m_start, m_end, m_store;
+      // ---- segmented sum over the source node, 64 message columns per round (rounds 0..3 = m.s * attention from the
+      // bf16 A tile, 4 = m.v[0:64], 5 = m.v[64:96]).  All 256 threads stage their 32 values of the round as float2
+      // pairs into a [128 rows][32 pair slots] buffer (slot index xor-swizzled with the row -> conflict-free 64-bit
+      // stores and loads); then warp w scans its 16 rows with lane = column pair: acc = keep*acc + x (keep = 0 at a
+      // segment start), and every segment end adds its partial sum to the aggregate row with one 8-byte reduction.
+      // (Row segments are cut at the 16-row windows, so all pieces go through RED.ADD; the aggregate rows are zero
+      // on entry — the node pass resets them.)
+      const int wr0 = warp * 16;
+      uint32_t m_start, m_end;
       {
-        const int rw = T.sRow[q0 + lane];
-        const int rp = lane > 0 ? T.sRow[q0 + lane - 1] : -2;
-        const int rn = lane < 31 ? T.sRow[q0 + lane + 1] : -2;
-        m_valid = __ballot_sync(0xffffffffu, rw >= 0);
-        m_start = __ballot_sync(0xffffffffu, rw != rp);
-        m_end = __ballot_sync(0xffffffffu, rw != rn);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, T.sB[q0 + lane] == 0);                     // row starts here
-        const uint32_t b1 = __ballot_sync(0xffffffffu, T.sB[q0 + lane] == T.sNa[q0 + lane] - 1);   // row ends here
-        // a segment may be STORED (not atomically added) iff it begins at its row's first edge and ends at its last
-        uint32_t ok = 0, cur_ok = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if ((m_start >> i) & 1u) cur_ok = (b0 >> i) & 1u;
-          if (((m_end >> i) & 1u) && cur_ok && ((b1 >> i) & 1u)) ok |= 1u << i;
-        }
-        m_store = ok;
+        const int li = lane & 15;
+        const int rw = T.sRow[wr0 + li];
+        const int rp = li > 0 ? T.sRow[wr0 + li - 1] : -2;
+        const int rn = li < 15 ? T.sRow[wr0 + li + 1] : -2;
+        m_start = __ballot_sync(0xffffffffu, rw != rp) & 0xffffu;
+        m_end = __ballot_sync(0xffffffffu, rw != rn && rw >= 0) & 0xffffu;
       }
-      const int nchunk = half == 0 ? 5 : 6;
-      for (int it = 0; it < nchunk; ++it) {
-        const int chunk = it < 4 ? half * 4 + it : (half == 0 ? 8 : 5 + it);
-        float v[32];
-        if (chunk < 8) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) x_load8(X, r, chunk * 32 + q * 8, v + q * 8);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= attn;
-        } else {
-          tmem_ld32(tl + TM_MV + (chunk - 8) * 32, v);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) T.sT[half][r][i] = v[i];
-        named_bar_sync(1 + half, TMT);
+      float2* sR2 = reinterpret_cast<float2*>(&T.sT[0][0][0]);
+      static_assert(TMT * 32 * 2 <= 2 * TMT * ST_LD, "reduction buffer");
+      for (int t = 0; t < 6; ++t) {
         {
-          float col[32];
+          float v[32];
+          if (t < 4) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) col[i] = T.sT[half][q0 + i][lane];
-          float acc = 0.f;
+            for (int q = 0; q < 4; ++q) x_load8(X, r, t * 64 + half * 32 + q * 8, v + q * 8);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            acc = ((m_start >> i) & 1u) ? col[i] : acc + col[i];
-            if (((m_end & m_valid) >> i) & 1u) {
-              float* dst = w.agg + (size_t)T.sRow[q0 + i] * kMsg + chunk * 32 + lane;
-              if ((m_store >> i) & 1u) *dst = acc;
-              else atomicAdd(dst, acc);
-            }
+            for (int i = 0; i < 32; ++i) v[i] *= attn;
+          } else if (t == 4) {
+            tmem_ld32(tl + TM_MV + half * 32, v);
+          } else {
+            tmem_ld8xN<2>(tl + TM_MV + 64 + half * 16, v);
+          }
+          if (t < 5) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sR2[r * 32 + half * 16 + (k ^ (r & 15))] = make_float2(v[2 * k], v[2 * k + 1]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sR2[r * 32 + ((half * 8 + k) ^ (r & 15))] = make_float2(v[2 * k], v[2 * k + 1]);
           }
         }
-        named_bar_sync(1 + half, TMT);
+        named_bar_sync(3, TC_EPI);
+        {
+          const bool active = t < 5 || lane < 16;
+          const int hb = (lane >> 4) * 16, kq = lane & 15;
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 x = sR2[(wr0 + i) * 32 + hb + (kq ^ i)];
+            const float keep = ((m_start >> i) & 1u) ? 0.f : 1.f;
+            acc = __ffma2_rn(make_float2(keep, keep), acc, x);
+            if (((m_end >> i) & 1u) && active)
+              atomicAdd(reinterpret_cast<float2*>(w.agg + (size_t)T.sRow[wr0 + i] * kMsg + t * 64 + 2 * lane), acc);
+          }
+        }
+        named_bar_sync(3, TC_EPI);
       }
       named_bar_sync(3, TC_EPI);       // sRow / exchange buffers free for the next tile
       if (tid == 0) BDIFF_STAMP(es++);
