@@ -679,6 +679,7 @@ void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const 
 // transposes (each thread reads/writes a contiguous 128-byte slice of its node's row).  Tensor work is replicated,
 // which is free: the tensor pipe is <10% busy in this pass.  Same MMA/TMA warps, blob and barriers as above.
 constexpr int R4M = 32;
+constexpr int NM_S1 = 256;        // second accumulator of the row-replicated kernel (overlaps U, see G4)
 
 // the small weights with the (mutually exclusive) next-layer / projection sets overlaid
 struct alignas(16) SmallWR4 {
@@ -698,7 +699,7 @@ struct NodeR4Tail {
   float sVD[R4M][49];      // vector_down of the feed-forward GCP (16 x 3)
   float sVP[R4M][25];      // vector_down of the position GCP (8 x 3)
   float sDot[8][R4M];
-  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full, wbar;
+  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full, wbar, u_free;
   uint32_t tmem_ptr;
 };
 constexpr size_t R4_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING + sizeof(NodeR4Tail) + 1024;
@@ -775,6 +776,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
     mbar_init(&T.a_ready, NT_EPI);
     mbar_init(&T.d_full, 1);
     mbar_init(&T.wbar, 1);
+    mbar_init(&T.u_free, NT_EPI);
     mbar_fence_init();
     SmallWR4& s = T.sw;
     auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
@@ -818,9 +820,20 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         push(256 * 128);                                  // G1c
         for (int j = 0; j < 4; ++j) push(256 * 128);      // G2
         for (int j = 0; j < 4; ++j) push(288 * 128);      // G3a (+ gate rows)
-        push(256 * 128);                                  // G3b
-        if (!last) { for (int j = 0; j < 8; ++j) push(256 * 128); }
-        else { for (int j = 0; j < 5; ++j) push(32 * 128); }
+        if (!last) {
+          // issue order G4 | G3b | G5 (G4 runs under E3a); blob order is G3b | G4 | G5
+          const size_t o3b = off;
+          off = o3b + 256 * 128;
+          for (int j = 0; j < 4; ++j) push(256 * 128);    // G4
+          const size_t o5 = off;
+          off = o3b;
+          push(256 * 128);                                // G3b
+          off = o5;
+          for (int j = 0; j < 4; ++j) push(256 * 128);    // G5
+        } else {
+          push(256 * 128);                                // G3b
+          for (int j = 0; j < 5; ++j) push(32 * 128);
+        }
       }
     }
   } else if (warp == 9) {
@@ -840,15 +853,16 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       };
       auto done_w = [&]() { umma_commit(&T.empty[ci % NSTAGES]); ++ci; };
       auto commit_d = [&]() { umma_commit(&T.d_full); BDIFF_STAMP(ms++); };
-      auto gemm256 = [&](bool fresh) {
+      auto gemm256 = [&](bool fresh, uint32_t dcol = NM_S) {
         for (int j = 0; j < 4; ++j) {
           const uint32_t wb = wait_w();
           for (int s = 0; s < 4; ++s)
-            umma_bf16(tmem + NM_S, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256,
+            umma_bf16(tmem + dcol, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256,
                       fresh ? (j | s) > 0 : true);
           done_w();
         }
       };
+      uint32_t pu = 0;
       auto gemm288 = [&](bool fresh_s, bool negate_u) {
         for (int j = 0; j < 4; ++j) {
           const uint32_t wb = wait_w();
@@ -872,11 +886,14 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         wait_a(); gemm288(false, true); gemm_extra(); commit_d();         // G1b/c: + h . W1b, U = -Wg h, + [vn|q] . W1c
         wait_a(); gemm256(true); commit_d();                              // G2: Y . W2
         wait_a(); gemm288(true, false); commit_d();                       // G3a: h_new . Wp, U += Wg h_new
-        wait_a(); gemm_extra(); commit_d();                               // G3b
         if (!last) {
-          wait_a(); gemm256(true); commit_d();                            // G4: h_new . Wsi(next)
-          wait_a(); gemm256(true); commit_d();                            // G5: h_new . Wsj(next)
+          // G4: h_new . Wsi(next) -> second accumulator (columns 256..511, over U) as soon as E3a has read U
+          mbar_wait_backoff(&T.u_free, pu); pu ^= 1; tc_fence_after();
+          gemm256(true, NM_S1);
+          wait_a(); gemm_extra(); commit_d();                             // G3b (the commit also covers G4)
+          wait_a(); gemm256(true); commit_d();                            // G5: h_new . Wsj(next), under E4
         } else {
+          wait_a(); gemm_extra(); commit_d();                             // G3b
           wait_a();                                                       // Gp: [h_new | vn | q] . Wproj -> U
           for (int j = 0; j < 5; ++j) {
             const uint32_t wb = wait_w();
@@ -1023,6 +1040,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       {
         float u8[8];
         tmem_ld8xN<1>(tl + NM_U + (s >> 1) * 8, u8);
+        if (!last) { tc_fence_before(); mbar_arrive(&T.u_free); }   // U consumed: G4 may overwrite its columns
         float vd[48];
 #pragma unroll
         for (int i = 0; i < 48; ++i) vd[i] = T.sVD[l][i];
@@ -1144,11 +1162,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
       }
       publish();
       if (!last) {
-        // ---- E4: PI scalar slice = S + b0; then the vector parts of PI / PJ: 2 x (hid0 + 3) outputs dealt round-robin
-        wait_d();
+        // ---- E4: PI scalar slice = S1 + b0 (G4 completed with the G3b commit; G5 is running into S meanwhile); then
+        //      the vector parts of PI / PJ: 2 x (hid0 + 3) outputs dealt round-robin
         {
           float v[32];
-          tmem_ld32(tl + NM_S + c0, v);
+          tmem_ld32(tl + NM_S1 + c0, v);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bb = *reinterpret_cast<const float4*>(&sw.u.nx.b0[c0 + q * 4]);
@@ -1156,7 +1174,6 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
           }
           warp_store_rows(T.sT[s], v, w.PI + (size_t)tile * R4M * kPStride + c0, kPStride, lane);
         }
-        publish();
         {
           // vector parts of PI / PJ for the next layer: 8 lanes per node (warp s: nodes 4s..4s+3), lane g takes
           // outputs g, g+8, ... of the 2 x (hid0 + 3) so that a store instruction touches 4 rows, not 32
