@@ -71,7 +71,6 @@ struct bdiff_handle {
   // tensor-core path state (bdiff_edge_tc.cu): per-layer pre-swizzled bf16 weight blobs
   DevBuf tc_blob, tc_node_blob;
   size_t tc_layer_bytes = 0, tc_node_layer_bytes = 0;
-  bool node_cluster = false;    // BDIFF_NODE_CLUSTER=1: 4-CTA cluster split of the node pass (measured: no faster)
   bool tc_dirty = true;
   int num_sms = 148;
 
@@ -241,15 +240,17 @@ cudaError_t ensure_work(bdiff_handle* h) {
   const size_t o_xi = take(Np * 3), o_x = take(Np * 3), o_hin = take(Np * d.Hin), o_chin = take(Np * 6),
                o_fbar = take(Np * 12), o_h = take(Np * 256), o_chi = take(Np * 96), o_PI = take(Np * kPStride),
                o_PJ = take(Np * kPStride), o_agg = take(Np * kMsg), o_hp = take(Np * 32),
-               o_e = take(Ep * d.Ed), o_xie = take(Ep * d.Xd * 3), o_fr = take(Ep * 9), o_sy = take(Np * 256),
-               o_sz = take(Np * 256), o_sd = take(Np * 8), o_flag = take(64);
+               o_e = take(Ep * d.Ed), o_xie = take(Ep * d.Xd * 3), o_fr = take(Ep * 9), o_pjt = take(Np * 256),
+               o_flag = take(64);
   cudaError_t e = h->work_buf.ensure(off * sizeof(float));
   if (e != cudaSuccess) return e;
   float* b = static_cast<float*>(h->work_buf.p);
   Work& w = h->work;
   w.x_init = b + o_xi; w.x = b + o_x; w.h_in = b + o_hin; w.chi_in = b + o_chin; w.fbar = b + o_fbar;
   w.h = b + o_h; w.chi = b + o_chi; w.PI = b + o_PI; w.PJ = b + o_PJ; w.agg = b + o_agg; w.hproj = b + o_hp;
-  w.e = b + o_e; w.xi = b + o_xie; w.frames = b + o_fr; w.scrY = b + o_sy; w.scrZ = b + o_sz; w.scrDot = b + o_sd;
+  w.e = b + o_e; w.xi = b + o_xie; w.frames = b + o_fr;
+  w.PJT = h->cfg.mode == BDIFF_MODE_TENSOR ? b + o_pjt : nullptr;
+  w.npad = (int)Np;
   w.nan_flag = reinterpret_cast<int*>(b + o_flag);
   w.dbg = nullptr;
   if (getenv("BDIFF_TIMING")) {
@@ -331,11 +332,8 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
     }
     e = tc_configure();
     if (e == cudaSuccess) e = tc_node_configure();
-    if (e == cudaSuccess) e = tc_node4_configure();
-    const char* nc = getenv("BDIFF_NODE_CLUSTER");
-    h->node_cluster = (nc && nc[0] == '1');
     h->tc_layer_bytes = tc_blob_bytes(d.Ed, d.Xd);
-    h->tc_node_layer_bytes = h->node_cluster ? tc_node4_blob_bytes() : tc_node_blob_bytes();
+    h->tc_node_layer_bytes = tc_node_blob_bytes();
     if (e == cudaSuccess) e = h->tc_blob.ensure(h->tc_layer_bytes * d.L);
     if (e == cudaSuccess) e = h->tc_node_blob.ensure(h->tc_node_layer_bytes * d.L);
   }
@@ -386,8 +384,7 @@ static void tc_prepare(bdiff_handle* h, cudaStream_t st) {
     launch_tc_pack(st, h->layers[l], h->d, static_cast<unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes);
     const int last = (l == h->d.L - 1);
     unsigned char* nb = static_cast<unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes;
-    if (h->node_cluster) launch_tc_pack_node4(st, h->layers[l], h->layers[last ? l : l + 1], h->embed, h->d, last, nb);
-    else launch_tc_pack_node(st, h->layers[l], h->layers[last ? l : l + 1], h->embed, h->d, last, nb);
+    launch_tc_pack_node(st, h->layers[l], h->layers[last ? l : l + 1], h->embed, h->d, last, nb);
     h->launches += 2;
   }
   h->tc_dirty = false;
@@ -558,11 +555,7 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
       launch_edge_message(st, p, d, h->layers[l], w);
     mark();
     const bool last = (l == d.L - 1);
-    if (tensor && h->node_cluster)
-      launch_node_update_tc4(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed,
-                             static_cast<const unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes, w,
-                             last ? 1 : 0, h->num_sms);
-    else if (tensor)
+    if (tensor)
       launch_node_update_tc(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed,
                             static_cast<const unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes, w,
                             last ? 1 : 0, h->num_sms);

@@ -585,53 +585,41 @@ __global__ void __launch_bounds__(TC_THREADS2, 1)
       publish();
 
       // ---- E0: m_0 = silu(S0 + P_i[row] + P_j[col]), this half's 128 columns in 4 rounds of 32.  P_i rows are
-      //      shared by consecutive edges (broadcast loads); P_j rows are gathered 8 lanes per row into sT[half].
-      //      The loads of round c+1 are in flight while round c is computed.
+      //      shared by consecutive edges (broadcast loads); the scalar part of P_j is stored column-major in blocks
+      //      of 32 nodes and the edges of a warp have consecutive target nodes, so a column load touches 1-3 lines.  The loads of round
+      //      c+1 are in flight while round c is computed.
       {
-        float4 buf[8], pa[8];
+        float4 pa[8];
+        float pj[32];
+        const int colj = rc.y;
+        const int cjn = colj < 0 ? 0 : colj;
+        const float* pjt = w.PJT + ((size_t)(cjn >> 5) * 256 + half * 128) * 32 + (cjn & 31);   // blocked layout
         auto prefetch = [&](int c) {
+          const float* pc = pjt + c * 1024;      // 32 columns x 32 nodes per round; immediate offsets below
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = i * TC_EPI + tid;
-            const int hh = idx >> 10, rr = (idx >> 3) & 127, c4 = idx & 7;
-            const int cj = T.sCol[rr];
-            buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (cj >= 0) buf[i] = *reinterpret_cast<const float4*>(w.PJ + (size_t)cj * kPStride + hh * 128 + c * 32 + c4 * 4);
-          }
+          for (int i = 0; i < 32; ++i) pj[i] = pc[i * 32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            pa[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row >= 0) pa[q] = *reinterpret_cast<const float4*>(pi + half * 128 + c * 32 + q * 4);
-          }
+          for (int q = 0; q < 8; ++q) pa[q] = *reinterpret_cast<const float4*>(pi + half * 128 + c * 32 + q * 4);
         };
         prefetch(0);
         wait_d();
         for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = i * TC_EPI + tid;
-            float* dst = &T.sT[idx >> 10][(idx >> 3) & 127][(idx & 7) * 4];
-            dst[0] = buf[i].x; dst[1] = buf[i].y; dst[2] = buf[i].z; dst[3] = buf[i].w;
-          }
           const int c0 = half * 128 + c * 32;
           float v[32];
           tmem_ld32(tl + TM_S + c0, v);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            v[q * 4 + 0] += pa[q].x; v[q * 4 + 1] += pa[q].y; v[q * 4 + 2] += pa[q].z; v[q * 4 + 3] += pa[q].w;
+            v[q * 4 + 0] += pa[q].x + pj[q * 4 + 0]; v[q * 4 + 1] += pa[q].y + pj[q * 4 + 1];
+            v[q * 4 + 2] += pa[q].z + pj[q * 4 + 2]; v[q * 4 + 3] += pa[q].w + pj[q * 4 + 3];
           }
-          named_bar_sync(3, TC_EPI);
           if (c < 3) prefetch(c + 1);
-          const float* pjs = &T.sT[half][r][0];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float2 p0 = silu_fast2(__fadd2_rn(make_float2(v[q * 4 + 0], v[q * 4 + 1]), make_float2(pjs[q * 4 + 0], pjs[q * 4 + 1])));
-            const float2 p1 = silu_fast2(__fadd2_rn(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(pjs[q * 4 + 2], pjs[q * 4 + 3])));
-            v[q * 4 + 0] = p0.x; v[q * 4 + 1] = p0.y; v[q * 4 + 2] = p1.x; v[q * 4 + 3] = p1.y;
+          for (int q = 0; q < 16; ++q) {
+            const float2 p0 = silu_fast2(make_float2(v[2 * q], v[2 * q + 1]));
+            v[2 * q] = p0.x; v[2 * q + 1] = p0.y;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) x_store8(X, r, c0 + q * 8, v + q * 8);
-          named_bar_sync(3, TC_EPI);
         }
       }
       publish();

@@ -19,14 +19,14 @@ struct Work {
   float* chi;      // [N,96]
   float* PI;       // [N,328] endpoint projections for the next edge pass (row side, bias folded in)
   float* PJ;       // [N,328] (col side)
+  float* PJT;      // [Npad/32][256][32] scalar part of PJ, column-major inside blocks of 32 nodes (tensor mode: consecutive
+                   //             edges of a tile have consecutive target nodes -> coalesced per-edge gather), else nullptr
+  int npad;        // row count of the padded node buffers
   float* agg;      // [N,352] aggregated messages
   float* hproj;    // [N,32]  projected scalar outputs (Hin used)
   float* e;        // [E,Ed]
   float* xi;       // [E,Xd*3]
   float* frames;   // [E,9]
-  float* scrY;     // [N,256] exchange scratch of the clustered node pass (silu(FF hidden))
-  float* scrZ;     // [N,256] exchange scratch (FF output Z2)
-  float* scrDot;   // [N,8]   partial dot products of the position-gate
   int* nan_flag;
   long long* dbg;  // optional [CTA][64] clock64 stamps of the tensor-core kernels (BDIFF_TIMING=1), else nullptr
 };
@@ -66,12 +66,6 @@ void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, co
                          unsigned char* blob);
 void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
-size_t tc_node4_blob_bytes();
-cudaError_t tc_node4_configure();
-void launch_tc_pack_node4(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
-                          unsigned char* blob);
-void launch_node_update_tc4(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
-                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
 void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
 
 }  // namespace bdiff

@@ -635,6 +635,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_node_embed(Plan p, Dims d, Embe
     w.chi[(size_t)(n0 + r) * 96 + c] = S.sV[r][c];
   }
   stage_next(S, d, wn, w, n0, ws);
+  if (w.PJT) {     // tensor mode: the edge pass gathers the scalar part of P_j column-major (see Work::PJT)
+    __syncthreads();
+    for (int idx = tid; idx < TMN * kH; idx += kThreads) {
+      const int c = idx / TMN, r = idx - c * TMN;
+      const int n = n0 + r;
+      w.PJT[((size_t)(n >> 5) * 256 + c) * 32 + (n & 31)] = w.PJ[(size_t)n * kPStride + c];
+    }
+  }
 }
 
 // Per layer, per node tile: feed-forward GCP2 on [aggregate | node], residual, mask, position-update GCP2,

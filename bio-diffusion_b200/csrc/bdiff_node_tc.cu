@@ -594,18 +594,14 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
             vrow[hid0 * 3 + ch * 3 + 0] = s0; vrow[hid0 * 3 + ch * 3 + 1] = s1; vrow[hid0 * 3 + ch * 3 + 2] = s2;
           }
         }
-        // ---- E5: PJ scalar part = S
+        // ---- E5: PJ scalar part = S, stored column-major in blocks of 32 nodes (lane = node -> 128 contiguous bytes per column)
         wait_d();
         for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
           float v[32];
           tmem_ld32(tl + NM_S + c0, v);
+          float* pb = w.PJT + ((size_t)(tile * 4 + (warp & 3)) * 256 + c0) * 32 + lane;   // block of 32 nodes = this warp's rows
 #pragma unroll
-          for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
-          __syncwarp();
-          float* pb = w.PJ + ((size_t)tile * NTM + row0) * kPStride + c0 + lane;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) pb[(size_t)i * kPStride] = tw[i][lane];
-          __syncwarp();
+          for (int i = 0; i < 32; ++i) pb[i * 32] = v[i];
         }
       } else {
         // ---- Ep: projected scalars = U + bias
@@ -1206,12 +1202,14 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
             vrow[0] = s0; vrow[1] = s1; vrow[2] = s2;
           }
         }
-        // ---- E5: PJ scalar slice = S
+        // ---- E5: PJ scalar slice = S, stored column-major (Work::PJT)
         wait_d();
         {
           float v[32];
           tmem_ld32(tl + NM_S + c0, v);
-          warp_store_rows(T.sT[s], v, w.PJ + (size_t)tile * R4M * kPStride + c0, kPStride, lane);
+          float* pb = w.PJT + ((size_t)tile * 256 + c0) * 32 + l;     // block = this tile's 32 nodes, lane = node
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pb[i * 32] = v[i];
         }
       } else {
         // ---- Ep: projected scalars = U + bias
@@ -1239,643 +1237,6 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
   }
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 512);
-}
-
-// ================================================================================================================
-// Clustered variant: each 128-node tile is shared by a thread-block CLUSTER of 4 CTAs; CTA `rank` owns output
-// columns [64*rank, 64*rank+64) of every 256-wide GEMM (N=64 MMAs, a quarter of every weight K-block), so a
-// QM9 batch (19 tiles) runs on 76 SMs instead of 19 and every phase is 4x shorter.  Operands that one phase
-// produces and the next consumes in full (silu(FF hidden), Z2, h_new, the position-gate dot product) are
-// exchanged through L2-resident global scratch, ordered by cluster-scope mbarrier arrives (remote arrive on the
-// peers' barrier via mapa) — no data goes through DSMEM.  Vector-channel work is replicated in the 4 CTAs
-// (thread-local, cheap); rank 0 owns the global writes of chi / x / projections.
-constexpr int NCL = 4;
-constexpr int N4_STAGE = 64 * 128;
-constexpr int N4_NST = 4;
-constexpr int M4_S = 0, M4_U = 64, M4_CHI = 96, M4_VDF = 192, M4_EX = 240;
-
-__host__ __device__ inline long long node4_rank_rows(int last) { return 64 * 13 + 4 * 32 + 64 * 5 + (last ? 5 * 32 : 8 * 64); }
-size_t tc_node4_blob_bytes() { return (size_t)NCL * node4_rank_rows(0) * 128; }
-
-__global__ void k_tc_pack_node4(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last, unsigned char* __restrict__ blob) {
-  const long long rr_total = node4_rank_rows(last);
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= NCL * rr_total * 64) return;
-  const int kc = (int)(idx % 64);
-  long long rowg = idx / 64;
-  const int rank = (int)(rowg / rr_total);
-  rowg -= (long long)rank * rr_total;
-  size_t base = (size_t)rank * node4_rank_rows(0) * 128;      // rank regions have the not-last size
-  float v = 0.f;
-  int r = 0;
-  auto seg = [&](long long nrows) -> bool {
-    if (rowg < nrows) return true;
-    rowg -= nrows;
-    base += (size_t)nrows * 128;
-    return false;
-  };
-  auto slice = [&](const float* W, int k0, int kmax) -> float {   // 4 chunks of 64 rows: W[(k0 + j*64 + kc)][64*rank + r]
-    const int j = (int)(rowg / 64);
-    r = (int)(rowg % 64);
-    base += (size_t)j * 64 * 128;
-    const int kk = k0 + j * 64 + kc;
-    return kk < kmax ? W[(size_t)kk * 256 + 64 * rank + r] : 0.f;
-  };
-  if (seg(4 * 64)) v = slice(lw.W1, 0, kKFF);
-  else if (seg(4 * 64)) v = slice(lw.W1, 256, kKFF);
-  else if (seg(64)) v = slice(lw.W1, 512, kKFF);
-  else if (seg(4 * 64)) v = slice(lw.W2, 0, 256);
-  else if (seg(4 * 32)) {
-    const int j = (int)(rowg / 32); r = (int)(rowg % 32); base += (size_t)j * 32 * 128;
-    v = lw.Wgf[(size_t)(j * 64 + kc) * 32 + r];
-  } else if (seg(4 * 64)) v = slice(lw.Wp, 0, kKM);
-  else if (seg(64)) v = slice(lw.Wp, 256, kKM);
-  else if (!last) {
-    if (seg(4 * 64)) v = slice(wn.Wsi, 0, 256);
-    else v = slice(wn.Wsj, 0, 256);
-  } else {
-    const int j = (int)(rowg / 32); r = (int)(rowg % 32); base += (size_t)j * 32 * 128;
-    const int kk = j * 64 + kc;
-    v = (kk < 300 && r < d.Hin) ? ew.pWs[(size_t)kk * d.Hin + r] : 0.f;
-  }
-  *reinterpret_cast<__nv_bfloat16*>(blob + base + sw128_offset(r, kc)) = __float2bfloat16_rn(v);
-}
-
-struct Node4Tail {
-  SmallWN sw;
-  float sTw[8][32][33];
-  float sMask[NTM];
-  uint64_t full[N4_NST], empty[N4_NST], a_ready, d_full, cbar, wbar;
-  uint32_t tmem_ptr;
-};
-constexpr size_t N4_SMEM_BYTES = 5 * (size_t)X_BLOCK + N4_NST * (size_t)N4_STAGE + sizeof(Node4Tail) + 1024;
-
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_barrier_all() {   // every thread of every CTA of the cluster
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t target_rank) {
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(target_rank)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-// staging from exchange scratch must not hit stale L1 lines: ld.global.cg
-__device__ __forceinline__ void stage_rows_cg(unsigned char* X, const float* __restrict__ base, int ld, int kk0, int wih,
-                                              int lane) {
-  const int kk = kk0 + lane * 4;
-#pragma unroll
-  for (int b = 0; b < 2; ++b) {
-    float4 v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      v[i] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(wih + 4 * (b * 16 + i)) * ld + lane * 4));
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      *reinterpret_cast<uint2*>(X + (kk >> 6) * X_BLOCK + sw128_offset(wih + 4 * (b * 16 + i), kk & 63)) =
-          make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-  }
-}
-
-__global__ void __cluster_dims__(NCL, 1, 1) __launch_bounds__(NT_THREADS, 1)
-    k_node_update_tc4(Plan p, Dims d, LayerW lw, LayerW wn, EmbedW ew, const unsigned char* __restrict__ blob_all, Work w,
-                      int last, int ntiles) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* X = smem;
-  unsigned char* ring = smem + 5 * X_BLOCK;
-  Node4Tail& T = *reinterpret_cast<Node4Tail*>(ring + N4_NST * N4_STAGE);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hid0 = d.hid0;
-  const int rank = (int)cluster_rank();
-  const int cl = blockIdx.x / NCL, ncl = gridDim.x / NCL;
-  const unsigned char* blob = blob_all + (size_t)rank * node4_rank_rows(0) * 128;
-
-  if (tid == 0) {
-    for (int i = 0; i < N4_NST; ++i) { mbar_init(&T.full[i], 1); mbar_init(&T.empty[i], 1); }
-    mbar_init(&T.a_ready, NT_EPI);
-    mbar_init(&T.d_full, 1);
-    mbar_init(&T.cbar, NCL);
-    mbar_fence_init();
-  }
-  if (warp == 8) tmem_alloc(&T.tmem_ptr, 512);
-  // small weights -> shared memory by TMA bulk copies (all in flight at once; sizes rounded up to 16 bytes, every
-  // packed array is 256-byte aligned and padded)
-  if (tid == 0) {
-    mbar_init(&T.wbar, 1);
-    mbar_fence_init();
-    SmallWN& s = T.sw;
-    auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
-    uint32_t total = sz(1024) + sz(192) + sz(512) + sz(32) + 2 * sz(256) + sz(256) + sz(96) + sz(8) + 2 * sz(256) + sz(1);
-    total += last ? sz(1024) + sz(96) + sz(d.Hin) : sz(256) + 2 * sz(32 * hid0) + 2 * sz(96);
-    mbar_expect_tx(&T.wbar, total);
-    auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &T.wbar); };
-    cp(s.Wdf, lw.Wdf, 64 * 16); cp(s.Wff, lw.Wff, 64 * 3); cp(s.Wuf, lw.Wuf, 16 * 32); cp(s.bgf, lw.bgf, 32);
-    cp(s.b1, lw.b1, 256); cp(s.b2, lw.b2, 256);
-    cp(s.Wdp, lw.Wdp, 32 * 8); cp(s.Wfp, lw.Wfp, 32 * 3); cp(s.Wup, lw.Wup, 8); cp(s.bp, lw.bp, 256);
-    cp(s.wgp, lw.Wgp, 256); cp(s.bgp, lw.bgp, 1);
-    if (!last) {
-      cp(s.b0, wn.b0, 256);
-      cp(s.Wd0i, wn.Wd0i, 32 * hid0); cp(s.Wd0j, wn.Wd0j, 32 * hid0); cp(s.Wf0i, wn.Wf0i, 96); cp(s.Wf0j, wn.Wf0j, 96);
-    } else {
-      cp(s.pWd, ew.pWd, 32 * 32); cp(s.pWf, ew.pWf, 96); cp(s.pbs, ew.pbs, d.Hin);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  cluster_barrier_all();          // every CTA's mbarriers are initialised before anybody arrives remotely
-  const uint32_t tmem = T.tmem_ptr;
-  if (warp < 8) mbar_wait(&T.wbar, 0);
-
-  if (warp == 8) {
-    if (lane == 0) {
-      uint32_t ci = 0;
-      for (int tile = cl; tile < ntiles; tile += ncl) {
-        size_t off = 0;
-        auto push = [&](uint32_t bytes) {
-          const uint32_t s = ci % N4_NST;
-          mbar_wait_backoff(&T.empty[s], ((ci / N4_NST) & 1) ^ 1);
-          mbar_expect_tx(&T.full[s], bytes);
-          bulk_g2s(ring + s * N4_STAGE, blob + off, bytes, &T.full[s]);
-          off += bytes;
-          ++ci;
-        };
-        for (int j = 0; j < 13; ++j) push(64 * 128);      // G1a, G1b, G1c, G2
-        for (int j = 0; j < 4; ++j) push(32 * 128);       // Gg
-        for (int j = 0; j < 5; ++j) push(64 * 128);       // G3a, G3b
-        if (!last) { for (int j = 0; j < 8; ++j) push(64 * 128); }
-        else { for (int j = 0; j < 5; ++j) push(32 * 128); }
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      const uint32_t i64 = umma_idesc_bf16(64, false), i32 = umma_idesc_bf16(32, false);
-      const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
-      uint32_t ci = 0, pa = 0;
-      auto wait_a = [&]() { mbar_wait_backoff(&T.a_ready, pa); pa ^= 1; tc_fence_after(); };
-      auto wait_w = [&]() -> uint32_t {
-        const uint32_t s = ci % N4_NST;
-        mbar_wait_backoff(&T.full[s], (ci / N4_NST) & 1);
-        tc_fence_after();
-        return raddr + s * N4_STAGE;
-      };
-      auto done_w = [&]() { umma_commit(&T.empty[ci % N4_NST]); ++ci; };
-      auto gemm64 = [&](bool fresh) {
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t wb = wait_w();
-          for (int s = 0; s < 4; ++s)
-            umma_bf16(tmem + M4_S, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i64,
-                      fresh ? (j | s) > 0 : true);
-          done_w();
-        }
-      };
-      auto gemm_extra = [&]() {
-        const uint32_t wb = wait_w();
-        for (int s = 0; s < 2; ++s)
-          umma_bf16(tmem + M4_S, umma_desc_sw128(xaddr + 4 * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i64, true);
-        done_w();
-      };
-      for (int tile = cl; tile < ntiles; tile += ncl) {
-        wait_a(); gemm64(true); umma_commit(&T.d_full);                    // G1a
-        wait_a(); gemm64(false); gemm_extra(); umma_commit(&T.d_full);     // G1b + G1c
-        wait_a(); gemm64(true); umma_commit(&T.d_full);                    // G2
-        wait_a();                                                          // Gg: U = Z2 . Wg (N=32)
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t wb = wait_w();
-          for (int s = 0; s < 4; ++s)
-            umma_bf16(tmem + M4_U, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i32,
-                      (j | s) > 0);
-          done_w();
-        }
-        umma_commit(&T.d_full);
-        wait_a(); gemm64(true); umma_commit(&T.d_full);                    // G3a
-        wait_a(); gemm_extra(); umma_commit(&T.d_full);                    // G3b
-        if (!last) {
-          wait_a(); gemm64(true); umma_commit(&T.d_full);                  // G4
-          wait_a(); gemm64(true); umma_commit(&T.d_full);                  // G5
-        } else {
-          wait_a();
-          for (int j = 0; j < 5; ++j) {
-            const uint32_t wb = wait_w();
-            const int ns = j < 4 ? 4 : 3;
-            for (int s = 0; s < ns; ++s)
-              umma_bf16(tmem + M4_U, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i32,
-                        (j | s) > 0);
-            done_w();
-          }
-          umma_commit(&T.d_full);
-        }
-      }
-    }
-  } else {
-    const int half = tid >> 7, r = tid & 127;
-    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const SmallWN& sw = T.sw;
-    const int cb = rank * 64 + half * 32;          // first of this thread's 32 output columns
-    uint32_t pd = 0, pc = 0;
-    auto wait_d = [&]() { mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); };
-    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); };
-    auto cluster_sync = [&]() {                    // all 4 CTAs' epilogue warps; orders their global writes
-      __threadfence();
-      named_bar_sync(3, NT_EPI);
-      if (tid == 0) {
-#pragma unroll
-        for (uint32_t q = 0; q < NCL; ++q) mbar_arrive_remote(&T.cbar, q);
-      }
-      mbar_wait_cluster(&T.cbar, pc);
-      pc ^= 1;
-    };
-    for (int tile = cl; tile < ntiles; tile += ncl) {
-      const int node = tile * NTM + r;
-      const bool valid = node < p.N;
-      const float m = (valid && p.mask[node]) ? 1.f : 0.f;
-      const int wih = warp & 3;
-      float (*tw)[33] = T.sTw[warp];
-      const int row0 = wih * 32;
-      const size_t trow = (size_t)tile * NTM;
-      if (half == 0) T.sMask[r] = m;
-      float* ag = w.agg + (size_t)node * kMsg;
-      float* crow = w.chi + (size_t)node * 96;
-      float f[9];
-      {
-        const float4 f0 = *reinterpret_cast<const float4*>(w.fbar + (size_t)node * 12);
-        const float4 f1 = *reinterpret_cast<const float4*>(w.fbar + (size_t)node * 12 + 4);
-        f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
-        f[8] = w.fbar[(size_t)node * 12 + 8];
-      }
-      // ---- T0 (replicated in the 4 CTAs): full agg_s -> A blocks 0..3; FF vector_down / vector_down_frames
-      stage_rows(X, w.agg + trow * kMsg + half * 128, kMsg, half * 128, wih, lane);
-      {
-        float vdh[24], vdf[9];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) vdh[i] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) vdf[i] = 0.f;
-#pragma unroll 4
-        for (int cc = 0; cc < 16; ++cc) {
-          const float* src = cc < 8 ? ag + kH + cc * 12 : crow + (cc - 8) * 12;
-          const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4),
-                       c = *reinterpret_cast<const float4*>(src + 8);
-          const float vin[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int ch = cc * 4 + j;
-            const float4 w0 = *reinterpret_cast<const float4*>(&sw.Wdf[ch * 16 + half * 8]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&sw.Wdf[ch * 16 + half * 8 + 4]);
-            const float wd[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-              vdh[h * 3 + 0] = fmaf(wd[h], vin[j * 3 + 0], vdh[h * 3 + 0]);
-              vdh[h * 3 + 1] = fmaf(wd[h], vin[j * 3 + 1], vdh[h * 3 + 1]);
-              vdh[h * 3 + 2] = fmaf(wd[h], vin[j * 3 + 2], vdh[h * 3 + 2]);
-            }
-            if (half == 0) {
-#pragma unroll
-              for (int q = 0; q < 3; ++q) {
-                const float wf = sw.Wff[ch * 3 + q];
-                vdf[q * 3 + 0] = fmaf(wf, vin[j * 3 + 0], vdf[q * 3 + 0]);
-                vdf[q * 3 + 1] = fmaf(wf, vin[j * 3 + 1], vdf[q * 3 + 1]);
-                vdf[q * 3 + 2] = fmaf(wf, vin[j * 3 + 2], vdf[q * 3 + 2]);
-              }
-            }
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 8; ++h)
-          x_store1(X, r, 256 + half * 8 + h, safe_norm3(vdh[h * 3], vdh[h * 3 + 1], vdh[h * 3 + 2]));
-#pragma unroll
-        for (int q = 0; q < 3; ++q) tmem_st8(tl + M4_VDF + half * 24 + q * 8, vdh + q * 8);
-        if (half == 0) {
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch)
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax)
-              x_store1(X, r, 256 + 16 + ch * 3 + ax,
-                       f[ax * 3] * vdf[ch * 3] + f[ax * 3 + 1] * vdf[ch * 3 + 1] + f[ax * 3 + 2] * vdf[ch * 3 + 2]);
-#pragma unroll
-          for (int i = 25; i < 32; ++i) x_store1(X, r, 256 + i, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const float4 a = *reinterpret_cast<const float4*>(crow + half * 48 + q * 8);
-          const float4 b = *reinterpret_cast<const float4*>(crow + half * 48 + q * 8 + 4);
-          const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-          tmem_st8(tl + M4_CHI + half * 48 + q * 8, v);
-        }
-      }
-      publish();
-      // ---- T0b: h -> A (after G1a consumed agg_s)
-      wait_d();
-      stage_rows(X, w.h + trow * kH + half * 128, kH, half * 128, wih, lane);
-      publish();
-      // ---- E1: this CTA's 64 columns of Y = silu(S + b1) -> scratch; exchange; full Y -> A
-      wait_d();
-      {
-        float v[32];
-        tmem_ld32(tl + M4_S + half * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tw[lane][i] = silu_fast(v[i] + sw.b1[cb + i]);
-        __syncwarp();
-        float* yb = w.scrY + (trow + row0) * 256 + cb + lane;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) yb[(size_t)i * 256] = tw[i][lane];
-        __syncwarp();
-      }
-      cluster_sync();
-      // every CTA has finished reading the tile's aggregate rows (T0): reset this CTA's quarter of them
-      for (int rr = rank * 32 + warp; rr < rank * 32 + 32; rr += 8) {
-        float4* z = reinterpret_cast<float4*>(w.agg + (trow + rr) * kMsg);
-        for (int c4 = lane; c4 < kMsg / 4; c4 += 32) z[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      stage_rows_cg(X, w.scrY + trow * 256 + half * 128, 256, half * 128, wih, lane);
-      publish();
-      // ---- E2a: Z2 slice -> scratch; h_new slice -> global h; exchange; full Z2 -> A (gate MMA)
-      wait_d();
-      {
-        float v[32];
-        tmem_ld32(tl + M4_S + half * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tw[lane][i] = v[i] + sw.b2[cb + i];
-        __syncwarp();
-        float* zb = w.scrZ + (trow + row0) * 256 + cb + lane;
-        float* hb = w.h + (trow + row0) * kH + cb + lane;
-#pragma unroll 8
-        for (int i = 0; i < 32; ++i) {
-          const float z = tw[i][lane];
-          zb[(size_t)i * 256] = z;
-          hb[(size_t)i * kH] = (hb[(size_t)i * kH] + z) * T.sMask[row0 + i];
-        }
-        __syncwarp();
-      }
-      cluster_sync();
-      stage_rows_cg(X, w.scrZ + trow * 256 + half * 128, 256, half * 128, wih, lane);
-      publish();
-      // ---- E2b: full h_new -> A
-      wait_d();
-      stage_rows_cg(X, w.h + trow * kH + half * 128, kH, half * 128, wih, lane);
-      publish();
-      // ---- E3a (replicated): FF gate, chi_new, vector_down of the position GCP -> A block 4
-      wait_d();
-      float vdp[24], vdfp[9];
-      {
-        float vdff[48], u[16], co[48], part[40];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) tmem_ld8(tl + M4_VDF + q * 8, vdff + q * 8);
-        tmem_ld8(tl + M4_U + half * 16, u);
-        tmem_ld8(tl + M4_U + half * 16 + 8, u + 8);
-#pragma unroll
-        for (int q = 0; q < 6; ++q) tmem_ld8(tl + M4_CHI + half * 48 + q * 8, co + q * 8);
-#pragma unroll
-        for (int i = 0; i < 40; ++i) part[i] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int o = half * 16 + j;
-          const float g = sigmoid_fast(u[j] + sw.bgf[o]);
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int h = 0; h < 16; ++h) {
-            const float wu = sw.Wuf[h * 32 + o];
-            s0 = fmaf(wu, vdff[h * 3 + 0], s0);
-            s1 = fmaf(wu, vdff[h * 3 + 1], s1);
-            s2 = fmaf(wu, vdff[h * 3 + 2], s2);
-          }
-          const float c0v = (co[j * 3 + 0] + s0 * g) * m, c1v = (co[j * 3 + 1] + s1 * g) * m,
-                      c2v = (co[j * 3 + 2] + s2 * g) * m;
-          co[j * 3 + 0] = c0v; co[j * 3 + 1] = c1v; co[j * 3 + 2] = c2v;
-          const float4 w0 = *reinterpret_cast<const float4*>(&sw.Wdp[o * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&sw.Wdp[o * 8 + 4]);
-          const float wd[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-          for (int h = 0; h < 8; ++h) {
-            part[h * 3 + 0] = fmaf(wd[h], c0v, part[h * 3 + 0]);
-            part[h * 3 + 1] = fmaf(wd[h], c1v, part[h * 3 + 1]);
-            part[h * 3 + 2] = fmaf(wd[h], c2v, part[h * 3 + 2]);
-          }
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const float wf = sw.Wfp[o * 3 + q];
-            part[24 + q * 3 + 0] = fmaf(wf, c0v, part[24 + q * 3 + 0]);
-            part[24 + q * 3 + 1] = fmaf(wf, c1v, part[24 + q * 3 + 1]);
-            part[24 + q * 3 + 2] = fmaf(wf, c2v, part[24 + q * 3 + 2]);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          tmem_st8(tl + M4_CHI + half * 48 + q * 8, co + q * 8);
-          if (rank == 0) {
-            *reinterpret_cast<float4*>(crow + half * 48 + q * 8) = make_float4(co[q * 8], co[q * 8 + 1], co[q * 8 + 2], co[q * 8 + 3]);
-            *reinterpret_cast<float4*>(crow + half * 48 + q * 8 + 4) =
-                make_float4(co[q * 8 + 4], co[q * 8 + 5], co[q * 8 + 6], co[q * 8 + 7]);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) tmem_st8(tl + M4_EX + half * 40 + q * 8, part + q * 8);
-        tc_fence_before();
-        named_bar_sync(3, NT_EPI);
-        tc_fence_after();
-        float other[40];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) tmem_ld8(tl + M4_EX + (half ^ 1) * 40 + q * 8, other + q * 8);
-#pragma unroll
-        for (int i = 0; i < 24; ++i) vdp[i] = part[i] + other[i];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) vdfp[i] = part[24 + i] + other[24 + i];
-        float a[16];
-        if (half == 0) {
-#pragma unroll
-          for (int h = 0; h < 8; ++h) a[h] = safe_norm3(vdp[h * 3], vdp[h * 3 + 1], vdp[h * 3 + 2]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ch = i / 3, ax = i - ch * 3;
-            a[8 + i] = f[ax * 3] * vdfp[ch * 3] + f[ax * 3 + 1] * vdfp[ch * 3 + 1] + f[ax * 3 + 2] * vdfp[ch * 3 + 2];
-          }
-        } else {
-          a[0] = f[6] * vdfp[6] + f[7] * vdfp[7] + f[8] * vdfp[8];
-#pragma unroll
-          for (int i = 1; i < 16; ++i) a[i] = 0.f;
-        }
-        x_store8(X, r, 256 + half * 16, a);
-        x_store8(X, r, 256 + half * 16 + 8, a + 8);
-      }
-      publish();
-      // ---- E3b: position gate: partial dot over this thread's 32 columns -> scratch; exchange; x update (rank 0)
-      wait_d();
-      {
-        float v[32];
-        tmem_ld32(tl + M4_S + half * 32, v);
-        float pdot = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pdot = fmaf(silu_fast(v[i] + sw.bp[cb + i]), sw.wgp[cb + i], pdot);
-        w.scrDot[(size_t)node * 8 + rank * 2 + half] = pdot;
-      }
-      cluster_sync();
-      if (rank == 0 && half == 0) {
-        const float4 d0 = __ldcg(reinterpret_cast<const float4*>(w.scrDot + (size_t)node * 8));
-        const float4 d1 = __ldcg(reinterpret_cast<const float4*>(w.scrDot + (size_t)node * 8 + 4));
-        const float gp = sigmoid_fast(((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w)) + sw.bgp[0]);
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-          float s = 0.f;
-#pragma unroll
-          for (int h = 0; h < 8; ++h) s = fmaf(sw.Wup[h], vdp[h * 3 + x], s);
-          const float xn = (w.x[(size_t)node * 3 + x] + s * gp) * m;
-          w.x[(size_t)node * 3 + x] = xn;
-          if (xn != xn) atomicExch(w.nan_flag, 1);
-        }
-      }
-      if (last) {
-        float chi[96];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) tmem_ld8(tl + M4_CHI + q * 8, chi + q * 8);
-        for (int h = half * 16; h < half * 16 + 16; ++h) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float wd = sw.pWd[c * 32 + h];
-            s0 = fmaf(wd, chi[c * 3 + 0], s0);
-            s1 = fmaf(wd, chi[c * 3 + 1], s1);
-            s2 = fmaf(wd, chi[c * 3 + 2], s2);
-          }
-          x_store1(X, r, 256 + h, safe_norm3(s0, s1, s2));
-        }
-        if (half == 0) {
-          for (int ch = 0; ch < 3; ++ch) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float wf = sw.pWf[c * 3 + ch];
-              s0 = fmaf(wf, chi[c * 3 + 0], s0);
-              s1 = fmaf(wf, chi[c * 3 + 1], s1);
-              s2 = fmaf(wf, chi[c * 3 + 2], s2);
-            }
-#pragma unroll
-            for (int ax = 0; ax < 3; ++ax)
-              x_store1(X, r, 256 + 32 + ch * 3 + ax, f[ax * 3] * s0 + f[ax * 3 + 1] * s1 + f[ax * 3 + 2] * s2);
-          }
-#pragma unroll
-          for (int i = 41; i < 48; ++i) x_store1(X, r, 256 + i, 0.f);
-        }
-      }
-      publish();
-      if (!last) {
-        // ---- E4: PI slice = S + b0; vector parts of PI / PJ by rank 0
-        wait_d();
-        {
-          float v[32];
-          tmem_ld32(tl + M4_S + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
-          __syncwarp();
-          float* pb = w.PI + (trow + row0) * kPStride + cb + lane;
-          const float b0v = sw.b0[cb + lane];
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) pb[(size_t)i * kPStride] = tw[i][lane] + b0v;
-          __syncwarp();
-        }
-        publish();
-        if (rank == 0) {
-          float chi[96];
-#pragma unroll
-          for (int q = 0; q < 12; ++q) tmem_ld8(tl + M4_CHI + q * 8, chi + q * 8);
-          float* vrow = (half == 0 ? w.PI : w.PJ) + (size_t)node * kPStride + kH;
-          const float* Wd = half == 0 ? sw.Wd0i : sw.Wd0j;
-          const float* Wf = half == 0 ? sw.Wf0i : sw.Wf0j;
-          for (int h = 0; h < hid0; ++h) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float wd = Wd[c * hid0 + h];
-              s0 = fmaf(wd, chi[c * 3 + 0], s0);
-              s1 = fmaf(wd, chi[c * 3 + 1], s1);
-              s2 = fmaf(wd, chi[c * 3 + 2], s2);
-            }
-            vrow[h * 3 + 0] = s0; vrow[h * 3 + 1] = s1; vrow[h * 3 + 2] = s2;
-          }
-          for (int ch = 0; ch < 3; ++ch) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float wf = Wf[c * 3 + ch];
-              s0 = fmaf(wf, chi[c * 3 + 0], s0);
-              s1 = fmaf(wf, chi[c * 3 + 1], s1);
-              s2 = fmaf(wf, chi[c * 3 + 2], s2);
-            }
-            vrow[hid0 * 3 + ch * 3 + 0] = s0; vrow[hid0 * 3 + ch * 3 + 1] = s1; vrow[hid0 * 3 + ch * 3 + 2] = s2;
-          }
-        }
-        // ---- E5: PJ slice = S
-        wait_d();
-        {
-          float v[32];
-          tmem_ld32(tl + M4_S + half * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) tw[lane][i] = v[i];
-          __syncwarp();
-          float* pb = w.PJ + (trow + row0) * kPStride + cb + lane;
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) pb[(size_t)i * kPStride] = tw[i][lane];
-          __syncwarp();
-        }
-      } else {
-        wait_d();
-        if (rank == 0 && half == 0) {
-          float v[32];
-          tmem_ld32(tl + M4_U, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < d.Hin) w.hproj[(size_t)node * 32 + i] = v[i] + sw.pbs[i];
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(3, NT_EPI);
-      tc_fence_after();
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  cluster_barrier_all();          // nobody exits while a peer may still arrive on its barrier
-  if (warp == 8) tmem_dealloc(tmem, 512);
-}
-
-cudaError_t tc_node4_configure() {
-  return cudaFuncSetAttribute(k_node_update_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)N4_SMEM_BYTES);
-}
-
-void launch_tc_pack_node4(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
-                          unsigned char* blob) {
-  const long long total = (long long)NCL * node4_rank_rows(last) * 64;
-  k_tc_pack_node4<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lw, wn, ew, d, last, blob);
-}
-
-void launch_node_update_tc4(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
-                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms) {
-  const int ntiles = (p.N + NTM - 1) / NTM;
-  const int max_clusters = num_sms / NCL;
-  const int clusters = ntiles < max_clusters ? ntiles : max_clusters;
-  k_node_update_tc4<<<clusters * NCL, NT_THREADS, N4_SMEM_BYTES, st>>>(p, d, lw, wn, ew, blob, w, last, ntiles);
 }
 
 }  // namespace bdiff
