@@ -11,19 +11,11 @@
 // TMEM columns: S 0..255 | U 256..287 | chi (96) 288..383 | VD_ff (48) 384..431 | pair exchange 2x40 432..511.
 #include "bdiff_kernels.h"
 #include "bdiff_tc.cuh"
+#include "bdiff_node_tc.cuh"
 
 namespace bdiff {
 
-#ifndef BDIFF_STAMP
-#define BDIFF_STAMP(slot) do { if (w.dbg && (slot) < 64) w.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
-#endif
 
-constexpr int NT_EPI = 256;
-constexpr int NT_THREADS = NT_EPI + 64;
-constexpr int NTM = 128;
-constexpr int NRING = 288 * 128;
-constexpr int NSTAGES = 2;
-constexpr int NM_S = 0, NM_U = 256, NM_CHI = 288, NM_VDF = 384, NM_EX = 432;
 
 size_t tc_node_blob_bytes() { return (size_t)(4 * 256 + 4 * 288 + 256 + 4 * 256 + 4 * 288 + 256 + 8 * 256) * 128; }
 
@@ -82,22 +74,11 @@ __global__ void k_tc_pack_node(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last
   *reinterpret_cast<__nv_bfloat16*>(blob + base + sw128_offset(r, kc)) = __float2bfloat16_rn(v);
 }
 
-struct alignas(16) SmallWN {
-  float Wdf[64 * 16], Wff[64 * 3], Wuf[16 * 32], bgf[32];
-  float b1[256], b2[256];
-  float Wdp[32 * 8], Wfp[32 * 3], Wup[8], bp[256], wgp[256], bgp[4];
-  float b0[256];
-  float Wd0i[32 * 20], Wd0j[32 * 20], Wf0i[32 * 3], Wf0j[32 * 3];
-  float pWd[32 * 32], pWf[32 * 3], pbs[32];
-};
-
-struct NodeTcTail {
+struct NodeTcTail : TcBars {
   SmallWN sw;
   float sTw[8][32][33];    // per-warp 32x32 transposition scratch (coalesced global stores of accumulator tiles)
   float sMask[NTM];
   float sDot[2][NTM];
-  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full, wbar;
-  uint32_t tmem_ptr;
 };
 
 constexpr size_t NT_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING + sizeof(NodeTcTail) + 1024;
@@ -633,12 +614,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
 
 __global__ void k_node_update_r4(Plan p, Dims d, LayerW lw, LayerW wn, EmbedW ew, const unsigned char* __restrict__ blob,
                                  Work w, int last, int ntiles);
-extern const size_t R4_SMEM_BYTES_V;
 
 cudaError_t tc_node_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_node_update_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NT_SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_node_update_r4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R4_SMEM_BYTES_V);
+  return cudaFuncSetAttribute(k_node_update_r4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R4_SMEM_BYTES);
 }
 
 void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
@@ -656,7 +636,7 @@ void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const 
   const int nt32 = (p.N + 31) / 32;
   if (force == 1 || (force < 0 && nt32 <= num_sms)) {
     const int grid = nt32 < num_sms ? nt32 : num_sms;
-    k_node_update_r4<<<grid, NT_THREADS, R4_SMEM_BYTES_V, st>>>(p, d, lw, wn, ew, blob, w, last, nt32);
+    k_node_update_r4<<<grid, NT_THREADS, R4_SMEM_BYTES, st>>>(p, d, lw, wn, ew, blob, w, last, nt32);
     return;
   }
   const int ntiles = (p.N + NTM - 1) / NTM;
@@ -674,91 +654,10 @@ void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const 
 // node l in its own lane quarter) and 1/8 of the vector-channel work; 4x more CTAs, 1/4 of the per-thread work, no
 // transposes (each thread reads/writes a contiguous 128-byte slice of its node's row).  Tensor work is replicated,
 // which is free: the tensor pipe is <10% busy in this pass.  Same MMA/TMA warps, blob and barriers as above.
-constexpr int R4M = 32;
-constexpr int NM_S1 = 256;        // second accumulator of the row-replicated kernel (overlaps U, see G4)
-
-// the small weights with the (mutually exclusive) next-layer / projection sets overlaid
-struct alignas(16) SmallWR4 {
-  float Wdf[64 * 16], Wff[64 * 3], Wuf[16 * 32], bgf[32];
-  float b1[256], b2[256];
-  float Wdp[32 * 8], Wfp[32 * 3], Wup[8], bp[256], wgp[256], bgp[4];
-  union {
-    struct { float b0[256], Wd0i[32 * 20], Wd0j[32 * 20], Wf0i[32 * 3], Wf0j[32 * 3]; } nx;
-    struct { float pWd[32 * 32], pWf[32 * 3], pbs[32]; } pj;
-  } u;
-};
-
-struct NodeR4Tail {
-  SmallWR4 sw;
-  float4 sT[8][16 * 8];    // per-warp 16 x 32 fp32 transposition scratch (xor-swizzled 16-byte chunks)
-  float sV[R4M][193];      // per node [agg_v (32x3) | chi (32x3)]; chi is replaced by chi_new in E3a
-  float sVD[R4M][49];      // vector_down of the feed-forward GCP (16 x 3)
-  float sVP[R4M][25];      // vector_down of the position GCP (8 x 3)
-  float sDot[8][R4M];
-  uint64_t full[NSTAGES], empty[NSTAGES], a_ready, d_full, wbar, u_free;
-  uint32_t tmem_ptr;
-};
-constexpr size_t R4_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING + sizeof(NodeR4Tail) + 1024;
-const size_t R4_SMEM_BYTES_V = R4_SMEM_BYTES;
-
-__device__ __forceinline__ void x_store8_rep4(unsigned char* X, int l, int kk, const float* v) {   // kk % 8 == 0
-  const uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  unsigned char* q = X + (kk >> 6) * X_BLOCK + sw128_offset(l, kk & 63);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(q + k * 4096) = u;
-}
-__device__ __forceinline__ void x_store1_rep4(unsigned char* X, int l, int kk, float v) {
-  const __nv_bfloat16 b = __float2bfloat16_rn(v);
-  unsigned char* q = X + (kk >> 6) * X_BLOCK + sw128_offset(l, kk & 63);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<__nv_bfloat16*>(q + k * 4096) = b;
-}
-
-// Global <-> "lane = row" register tiles through the per-warp scratch, so that every global instruction touches 4
-// rows x 128 contiguous bytes instead of 32 rows x 16 bytes (the L1 processes one line tag per cycle).
-// v[32] = this lane's row (32 consecutive floats); gbase -> (row 0, first column) of the warp's 32 x 32 block.
-__device__ __forceinline__ void warp_store_rows(float4* sc, const float* v, float* gbase, int ld, int lane) {
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    if ((lane >> 4) == pass) {
-      const int r = lane & 15;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sc[r * 8 + (j ^ (r & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = 4 * i + (lane >> 3);
-      const float4 t = sc[r * 8 + ((lane & 7) ^ (r & 7))];
-      *reinterpret_cast<float4*>(gbase + (size_t)(pass * 16 + r) * ld + (lane & 7) * 4) = t;
-    }
-    __syncwarp();
-  }
-}
-__device__ __forceinline__ void warp_load_rows(float4* sc, float* v, const float4* t, int lane) {   // t[8]: see caller
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = 4 * i + (lane >> 3);
-      sc[r * 8 + ((lane & 7) ^ (r & 7))] = t[pass * 4 + i];
-    }
-    __syncwarp();
-    if ((lane >> 4) == pass) {
-      const int r = lane & 15;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 x = sc[r * 8 + (j ^ (r & 7))];
-        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-      }
-    }
-    __syncwarp();
-  }
-}
-
 __global__ void __launch_bounds__(NT_THREADS, 1)
     k_node_update_r4(Plan p, Dims d, LayerW lw, LayerW wn, EmbedW ew, const unsigned char* __restrict__ blob, Work w,
                      int last, int ntiles) {
+  constexpr int NSTRIDE = NRING;      // ring stage stride (the layer megakernel uses the edge pass's larger stage)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* X = smem;
@@ -802,34 +701,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
     if (lane == 0) {
       uint32_t ci = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        size_t off = 0;
-        auto push = [&](uint32_t bytes) {
-          const uint32_t s = ci % NSTAGES;
-          mbar_wait_backoff(&T.empty[s], ((ci / NSTAGES) & 1) ^ 1);
-          mbar_expect_tx(&T.full[s], bytes);
-          bulk_g2s(ring + s * NRING, blob + off, bytes, &T.full[s]);
-          off += bytes;
-          ++ci;
-        };
-        for (int j = 0; j < 4; ++j) push(256 * 128);      // G1a
-        for (int j = 0; j < 4; ++j) push(288 * 128);      // G1b (+ gate rows)
-        push(256 * 128);                                  // G1c
-        for (int j = 0; j < 4; ++j) push(256 * 128);      // G2
-        for (int j = 0; j < 4; ++j) push(288 * 128);      // G3a (+ gate rows)
-        if (!last) {
-          // issue order G4 | G3b | G5 (G4 runs under E3a); blob order is G3b | G4 | G5
-          const size_t o3b = off;
-          off = o3b + 256 * 128;
-          for (int j = 0; j < 4; ++j) push(256 * 128);    // G4
-          const size_t o5 = off;
-          off = o3b;
-          push(256 * 128);                                // G3b
-          off = o5;
-          for (int j = 0; j < 4; ++j) push(256 * 128);    // G5
-        } else {
-          push(256 * 128);                                // G3b
-          for (int j = 0; j < 5; ++j) push(32 * 128);
-        }
+#include "node_r4_tile_producer.inc"
       }
     }
   } else if (warp == 9) {
@@ -878,29 +750,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
         done_w();
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        wait_a(); gemm256(true); commit_d();                              // G1a: agg_s . W1a
-        wait_a(); gemm288(false, true); gemm_extra(); commit_d();         // G1b/c: + h . W1b, U = -Wg h, + [vn|q] . W1c
-        wait_a(); gemm256(true); commit_d();                              // G2: Y . W2
-        wait_a(); gemm288(true, false); commit_d();                       // G3a: h_new . Wp, U += Wg h_new
-        if (!last) {
-          // G4: h_new . Wsi(next) -> second accumulator (columns 256..511, over U) as soon as E3a has read U
-          mbar_wait_backoff(&T.u_free, pu); pu ^= 1; tc_fence_after();
-          gemm256(true, NM_S1);
-          wait_a(); gemm_extra(); commit_d();                             // G3b (the commit also covers G4)
-          wait_a(); gemm256(true); commit_d();                            // G5: h_new . Wsj(next), under E4
-        } else {
-          wait_a(); gemm_extra(); commit_d();                             // G3b
-          wait_a();                                                       // Gp: [h_new | vn | q] . Wproj -> U
-          for (int j = 0; j < 5; ++j) {
-            const uint32_t wb = wait_w();
-            const int ns = j < 4 ? 4 : 3;
-            for (int s = 0; s < ns; ++s)
-              umma_bf16(tmem + NM_U, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i32,
-                        (j | s) > 0);
-            done_w();
-          }
-          commit_d();
-        }
+#include "node_r4_tile_mma.inc"
       }
     }
   } else {
@@ -914,324 +764,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1)
     auto wait_d = [&]() { if (tid == 0) BDIFF_STAMP(es++); mbar_wait(&T.d_full, pd); pd ^= 1; tc_fence_after(); if (tid == 0) BDIFF_STAMP(es++); };
     auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&T.a_ready); if (tid == 0) BDIFF_STAMP(es++); };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      if (tid == 0) BDIFF_STAMP(es++);
-      const int node = tile * R4M + l;
-      const float m = (node < p.N && p.mask[node]) ? 1.f : 0.f;
-      float hreg[32];
-      // ---- T0a: aggregate scalars -> A (4 replicas), coalesced: warp s stages nodes 4s..4s+3, one instruction per
-      //      contiguous 512-byte half row (any thread may write any A row); prefetch this thread's own 32 h scalars
-      {
-        float4 a[8], hh[8];
-        const float* abase = w.agg + ((size_t)tile * R4M + 4 * s) * kMsg + lane * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(abase + (size_t)(i >> 1) * kMsg + (i & 1) * 128);
-        const float* hbase = w.h + (size_t)tile * R4M * kH + c0 + (lane & 7) * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hh[i] = *reinterpret_cast<const float4*>(hbase + (size_t)(4 * i + (lane >> 3)) * kH);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int kk = (i & 1) * 128 + lane * 4;
-          const uint2 u = make_uint2(pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i].z, a[i].w));
-          unsigned char* q = X + (kk >> 6) * X_BLOCK + sw128_offset(4 * s + (i >> 1), kk & 63);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint2*>(q + k * 4096) = u;
-        }
-        publish();
-        warp_load_rows(T.sT[s], hreg, hh, lane);
-      }
-      // ---- T0 vectors (overlaps G1a): stage [agg_v | chi] of the 32 nodes (coalesced: 8 lanes per node row), then
-      //      vector_down / vector_down_frames of the FF GCP split by OUTPUT: warp s computes hidden channels 2s, 2s+1
-      //      (and frame channel s if s < 3)
-      float f[9];
-      {
-        const float4 f0 = *reinterpret_cast<const float4*>(w.fbar + (size_t)node * 12);
-        const float4 f1 = *reinterpret_cast<const float4*>(w.fbar + (size_t)node * 12 + 4);
-        f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
-        f[8] = w.fbar[(size_t)node * 12 + 8];
-        const int rr = 4 * s + (lane >> 3), g = lane & 7;
-        const size_t nr = (size_t)tile * R4M + rr;
-        float4 v[6];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          v[i] = *reinterpret_cast<const float4*>(w.agg + nr * kMsg + kH + (g + 8 * i) * 4);
-          v[3 + i] = *reinterpret_cast<const float4*>(w.chi + nr * 96 + (g + 8 * i) * 4);
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          float* dst = &T.sV[rr][(i / 3) * 96 + (g + 8 * (i % 3)) * 4];
-          dst[0] = v[i].x; dst[1] = v[i].y; dst[2] = v[i].z; dst[3] = v[i].w;
-        }
-      }
-      named_bar_sync(1, NT_EPI);
-      {
-        float a0[3] = {0.f, 0.f, 0.f}, a1[3] = {0.f, 0.f, 0.f}, af[3] = {0.f, 0.f, 0.f};
-        const float* vr = T.sV[l];
-#pragma unroll 8
-        for (int ch = 0; ch < 64; ++ch) {
-          const float vx = vr[ch * 3], vy = vr[ch * 3 + 1], vz = vr[ch * 3 + 2];
-          const float2 wd = *reinterpret_cast<const float2*>(&sw.Wdf[ch * 16 + 2 * s]);
-          a0[0] = fmaf(wd.x, vx, a0[0]); a0[1] = fmaf(wd.x, vy, a0[1]); a0[2] = fmaf(wd.x, vz, a0[2]);
-          a1[0] = fmaf(wd.y, vx, a1[0]); a1[1] = fmaf(wd.y, vy, a1[1]); a1[2] = fmaf(wd.y, vz, a1[2]);
-          if (s < 3) {
-            const float wf = sw.Wff[ch * 3 + s];
-            af[0] = fmaf(wf, vx, af[0]); af[1] = fmaf(wf, vy, af[1]); af[2] = fmaf(wf, vz, af[2]);
-          }
-        }
-        float* vd = &T.sVD[l][s * 6];
-        vd[0] = a0[0]; vd[1] = a0[1]; vd[2] = a0[2]; vd[3] = a1[0]; vd[4] = a1[1]; vd[5] = a1[2];
-        x_store1_rep4(X, l, 256 + 2 * s, safe_norm3(a0[0], a0[1], a0[2]));
-        x_store1_rep4(X, l, 256 + 2 * s + 1, safe_norm3(a1[0], a1[1], a1[2]));
-        if (s < 3) {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax)
-            x_store1_rep4(X, l, 256 + 16 + s * 3 + ax, f[ax * 3] * af[0] + f[ax * 3 + 1] * af[1] + f[ax * 3 + 2] * af[2]);
-        } else if (s == 3) {
-#pragma unroll
-          for (int i = 25; i < 32; ++i) x_store1_rep4(X, l, 256 + i, 0.f);
-        }
-      }
-      // ---- T0b: h -> A blocks 0..3 (after G1a has consumed agg_s)
-      wait_d();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) x_store8_rep4(X, l, c0 + q * 8, hreg + q * 8);
-      publish();
-      // ---- E1: Y = silu(S + b1)
-      wait_d();
-      {
-        float v[32];
-        tmem_ld32(tl + NM_S + c0, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(&sw.b1[c0 + q * 4]);
-          v[q * 4 + 0] = silu_fast(v[q * 4 + 0] + bb.x);
-          v[q * 4 + 1] = silu_fast(v[q * 4 + 1] + bb.y);
-          v[q * 4 + 2] = silu_fast(v[q * 4 + 2] + bb.z);
-          v[q * 4 + 3] = silu_fast(v[q * 4 + 3] + bb.w);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) x_store8_rep4(X, l, c0 + q * 8, v + q * 8);
-      }
-      publish();
-      // ---- E2: h_new = (h + S + b2) * mask -> global h (fp32, contiguous 128-byte slice) and bf16 into A
-      wait_d();
-      {
-        float v[32];
-        tmem_ld32(tl + NM_S + c0, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(&sw.b2[c0 + q * 4]);
-          v[q * 4 + 0] = (hreg[q * 4 + 0] + v[q * 4 + 0] + bb.x) * m;
-          v[q * 4 + 1] = (hreg[q * 4 + 1] + v[q * 4 + 1] + bb.y) * m;
-          v[q * 4 + 2] = (hreg[q * 4 + 2] + v[q * 4 + 2] + bb.z) * m;
-          v[q * 4 + 3] = (hreg[q * 4 + 3] + v[q * 4 + 3] + bb.w) * m;
-        }
-        warp_store_rows(T.sT[s], v, w.h + (size_t)tile * R4M * kH + c0, kH, lane);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) x_store8_rep4(X, l, c0 + q * 8, v + q * 8);
-      }
-      publish();
-      // ---- E3a: FF vector gate and chi_new for vector channels 4s..4s+3, then vector_down of the position GCP
-      //      (hidden channel s, frame channel s if s < 3)
-      wait_d();
-      {
-        float u8[8];
-        tmem_ld8xN<1>(tl + NM_U + (s >> 1) * 8, u8);
-        if (!last) { tc_fence_before(); mbar_arrive(&T.u_free); }   // U consumed: G4 may overwrite its columns
-        float vd[48];
-#pragma unroll
-        for (int i = 0; i < 48; ++i) vd[i] = T.sVD[l][i];
-        float* cr = &T.sV[l][96 + s * 12];
-        float cn[12];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int o = s * 4 + j;
-          const float uj = (s & 1) ? u8[4 + j] : u8[j];
-          const float g = sigmoid_fast(uj + sw.bgf[o]);
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int h = 0; h < 16; ++h) {
-            const float wu = sw.Wuf[h * 32 + o];
-            s0 = fmaf(wu, vd[h * 3 + 0], s0);
-            s1 = fmaf(wu, vd[h * 3 + 1], s1);
-            s2 = fmaf(wu, vd[h * 3 + 2], s2);
-          }
-          cn[j * 3 + 0] = (cr[j * 3 + 0] + s0 * g) * m;
-          cn[j * 3 + 1] = (cr[j * 3 + 1] + s1 * g) * m;
-          cn[j * 3 + 2] = (cr[j * 3 + 2] + s2 * g) * m;
-        }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) cr[i] = cn[i];
-        float* crow = w.chi + (size_t)node * 96 + s * 12;
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          *reinterpret_cast<float4*>(crow + q * 4) = make_float4(cn[q * 4], cn[q * 4 + 1], cn[q * 4 + 2], cn[q * 4 + 3]);
-      }
-      named_bar_sync(1, NT_EPI);
-      {
-        const float* cv = &T.sV[l][96];
-        float a[3] = {0.f, 0.f, 0.f}, af[3] = {0.f, 0.f, 0.f};
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-          const float vx = cv[c * 3], vy = cv[c * 3 + 1], vz = cv[c * 3 + 2];
-          const float wd = sw.Wdp[c * 8 + s];
-          a[0] = fmaf(wd, vx, a[0]); a[1] = fmaf(wd, vy, a[1]); a[2] = fmaf(wd, vz, a[2]);
-          if (s < 3) {
-            const float wf = sw.Wfp[c * 3 + s];
-            af[0] = fmaf(wf, vx, af[0]); af[1] = fmaf(wf, vy, af[1]); af[2] = fmaf(wf, vz, af[2]);
-          }
-        }
-        float* vp = &T.sVP[l][s * 3];
-        vp[0] = a[0]; vp[1] = a[1]; vp[2] = a[2];
-        x_store1_rep4(X, l, 256 + s, safe_norm3(a[0], a[1], a[2]));
-        if (s < 3) {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax)
-            x_store1_rep4(X, l, 256 + 8 + s * 3 + ax, f[ax * 3] * af[0] + f[ax * 3 + 1] * af[1] + f[ax * 3 + 2] * af[2]);
-        } else if (s == 3) {
-#pragma unroll
-          for (int i = 17; i < 32; ++i) x_store1_rep4(X, l, 256 + i, 0.f);
-        }
-      }
-      publish();
-      // ---- E3b: position GCP: gate = sigmoid(wg . silu(S + bp) + bg), x += (Wu . VD) * gate
-      wait_d();
-      {
-        float v[32];
-        tmem_ld32(tl + NM_S + c0, v);
-        float pdot = 0.f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = *reinterpret_cast<const float4*>(&sw.bp[c0 + q * 4]);
-          const float4 wg = *reinterpret_cast<const float4*>(&sw.wgp[c0 + q * 4]);
-          pdot = fmaf(silu_fast(v[q * 4 + 0] + bb.x), wg.x, pdot);
-          pdot = fmaf(silu_fast(v[q * 4 + 1] + bb.y), wg.y, pdot);
-          pdot = fmaf(silu_fast(v[q * 4 + 2] + bb.z), wg.z, pdot);
-          pdot = fmaf(silu_fast(v[q * 4 + 3] + bb.w), wg.w, pdot);
-        }
-        T.sDot[s][l] = pdot;
-        named_bar_sync(1, NT_EPI);
-        if (s == 0) {
-          float tot = sw.bgp[0];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) tot += T.sDot[k][l];
-          const float gp = sigmoid_fast(tot);
-#pragma unroll
-          for (int x = 0; x < 3; ++x) {
-            float acc = 0.f;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) acc = fmaf(sw.Wup[h], T.sVP[l][h * 3 + x], acc);
-            const float xn = (w.x[(size_t)node * 3 + x] + acc * gp) * m;
-            w.x[(size_t)node * 3 + x] = xn;
-            if (xn != xn) atomicExch(w.nan_flag, 1);
-          }
-        }
-      }
-      if (last) {
-        // projection GCP2 (256,32)->(Hin,0): [vn(32) | q(9) | 0] -> A block 4 columns 0..47; warp s: hidden 4s..4s+3
-        const float* cv = &T.sV[l][96];
-        float acc[12], af[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 12; ++i) acc[i] = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-          const float vx = cv[c * 3], vy = cv[c * 3 + 1], vz = cv[c * 3 + 2];
-          const float4 wd = *reinterpret_cast<const float4*>(&sw.u.pj.pWd[c * 32 + 4 * s]);
-          acc[0] = fmaf(wd.x, vx, acc[0]); acc[1] = fmaf(wd.x, vy, acc[1]); acc[2] = fmaf(wd.x, vz, acc[2]);
-          acc[3] = fmaf(wd.y, vx, acc[3]); acc[4] = fmaf(wd.y, vy, acc[4]); acc[5] = fmaf(wd.y, vz, acc[5]);
-          acc[6] = fmaf(wd.z, vx, acc[6]); acc[7] = fmaf(wd.z, vy, acc[7]); acc[8] = fmaf(wd.z, vz, acc[8]);
-          acc[9] = fmaf(wd.w, vx, acc[9]); acc[10] = fmaf(wd.w, vy, acc[10]); acc[11] = fmaf(wd.w, vz, acc[11]);
-          if (s < 3) {
-            const float wf = sw.u.pj.pWf[c * 3 + s];
-            af[0] = fmaf(wf, vx, af[0]); af[1] = fmaf(wf, vy, af[1]); af[2] = fmaf(wf, vz, af[2]);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) x_store1_rep4(X, l, 256 + 4 * s + k, safe_norm3(acc[k * 3], acc[k * 3 + 1], acc[k * 3 + 2]));
-        if (s < 3) {
-#pragma unroll
-          for (int ax = 0; ax < 3; ++ax)
-            x_store1_rep4(X, l, 256 + 32 + s * 3 + ax, f[ax * 3] * af[0] + f[ax * 3 + 1] * af[1] + f[ax * 3 + 2] * af[2]);
-        } else if (s == 3) {
-#pragma unroll
-          for (int i = 41; i < 48; ++i) x_store1_rep4(X, l, 256 + i, 0.f);
-        }
-      }
-      publish();
-      if (!last) {
-        // ---- E4: PI scalar slice = S1 + b0 (G4 completed with the G3b commit; G5 is running into S meanwhile); then
-        //      the vector parts of PI / PJ: 2 x (hid0 + 3) outputs dealt round-robin
-        {
-          float v[32];
-          tmem_ld32(tl + NM_S1 + c0, v);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bb = *reinterpret_cast<const float4*>(&sw.u.nx.b0[c0 + q * 4]);
-            v[q * 4] += bb.x; v[q * 4 + 1] += bb.y; v[q * 4 + 2] += bb.z; v[q * 4 + 3] += bb.w;
-          }
-          warp_store_rows(T.sT[s], v, w.PI + (size_t)tile * R4M * kPStride + c0, kPStride, lane);
-        }
-        {
-          // vector parts of PI / PJ for the next layer: 8 lanes per node (warp s: nodes 4s..4s+3), lane g takes
-          // outputs g, g+8, ... of the 2 x (hid0 + 3) so that a store instruction touches 4 rows, not 32
-          const int rr = 4 * s + (lane >> 3), g = lane & 7;
-          const size_t nr = (size_t)tile * R4M + rr;
-          float chi[96];
-#pragma unroll
-          for (int i = 0; i < 96; ++i) chi[i] = T.sV[rr][96 + i];
-          const int nout = hid0 + 3;
-          for (int k = g; k < 2 * nout; k += 8) {
-            const bool isj = k >= nout;
-            const int kk = isj ? k - nout : k;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-            if (kk < hid0) {
-              const float* Wd = (isj ? sw.u.nx.Wd0j : sw.u.nx.Wd0i) + kk;
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const float wd = Wd[c * hid0];
-                s0 = fmaf(wd, chi[c * 3 + 0], s0); s1 = fmaf(wd, chi[c * 3 + 1], s1); s2 = fmaf(wd, chi[c * 3 + 2], s2);
-              }
-            } else {
-              const float* Wf = (isj ? sw.u.nx.Wf0j : sw.u.nx.Wf0i) + (kk - hid0);
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const float wf = Wf[c * 3];
-                s0 = fmaf(wf, chi[c * 3 + 0], s0); s1 = fmaf(wf, chi[c * 3 + 1], s1); s2 = fmaf(wf, chi[c * 3 + 2], s2);
-              }
-            }
-            float* vrow = (isj ? w.PJ : w.PI) + nr * kPStride + kH + kk * 3;
-            vrow[0] = s0; vrow[1] = s1; vrow[2] = s2;
-          }
-        }
-        // ---- E5: PJ scalar slice = S, stored column-major (Work::PJT)
-        wait_d();
-        {
-          float v[32];
-          tmem_ld32(tl + NM_S + c0, v);
-          float* pb = w.PJT + ((size_t)tile * 256 + c0) * 32 + l;     // block = this tile's 32 nodes, lane = node
-#pragma unroll
-          for (int i = 0; i < 32; ++i) pb[i * 32] = v[i];
-        }
-      } else {
-        // ---- Ep: projected scalars = U + bias
-        wait_d();
-        if (s == 0) {
-          float v[32];
-          tmem_ld32(tl + NM_U, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < d.Hin) w.hproj[(size_t)node * 32 + i] = v[i] + sw.u.pj.pbs[i];
-        }
-      }
-      // reset this node's aggregate row for the next layer's edge pass (every read of it happened before the first
-      // accumulator wait of this tile)
-      {
-        float4* z = reinterpret_cast<float4*>(w.agg + ((size_t)tile * R4M + 4 * s) * kMsg);   // 4 rows = 352 float4
-#pragma unroll
-        for (int i = 0; i < 11; ++i) z[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      tc_fence_before();
-      named_bar_sync(1, NT_EPI);     // everybody is done with S / U / staging buffers before the next tile
-      tc_fence_after();
+#include "node_r4_tile_epilogue.inc"
     }
     tc_fence_before();
   }
