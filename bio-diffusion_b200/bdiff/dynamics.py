@@ -224,7 +224,19 @@ class GCPNetDynamicsB200(nn.Module):
             self._handle, self._stream(), C.c_void_p(xh_c.data_ptr()), C.c_void_p(t_c.data_ptr()), ctx_ptr,
             C.c_void_p(out.data_ptr()), ms), "bdiff_profile_forward")
         names = ("prep", "edge_embed", "node_embed", "edge_message", "node_update", "finalize", "total")
-        return {k: float(ms[i]) for i, k in enumerate(names)}, out
+        prof = {k: float(ms[i]) for i, k in enumerate(names)}
+        if ms[7] < 0:       # tensor mode default: all layers ran as ONE persistent kernel (k_layers_tc)
+            prof["layers_fused"] = prof.pop("edge_message")
+            prof.pop("node_update")
+        return prof, out
+
+    @property
+    def kernels_per_forward(self) -> int:
+        """libbdiff kernels in one denoiser forward: prep, node_frames, edge_embed, node_embed, finalize plus either
+        one persistent k_layers_tc (tensor mode) or 2 per layer (parity mode, or BDIFF_MEGA=0)."""
+        import os
+        fused = self.mode == "tensor" and os.environ.get("BDIFF_MEGA", "1")[:1] != "0"
+        return 5 + (1 if fused else 2 * self.cfg.num_layers)
 
     def launch_count(self) -> int:
         return int(_lib.load().bdiff_launch_count(self._handle)) if self._handle is not None else 0

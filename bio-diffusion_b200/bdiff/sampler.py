@@ -135,7 +135,7 @@ class GCDMSampler:
                 st["step"].add_(1)
 
         # one forward = prep, node_frames, edge_embed, node_embed, L x (edge_message, node_update), finalize
-        per_forward = 5 + 2 * cfg.num_layers
+        per_forward = self.net.kernels_per_forward
         self.kernel_launches += 1 + steps * (per_forward + 1) + (per_forward + 1)
         # p(x, h | z_0)  (variational_diffusion.py:1378-1387, 840-907)
         z0 = st["z"].clone() if return_z0 else None

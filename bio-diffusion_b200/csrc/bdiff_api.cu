@@ -1,11 +1,13 @@
 // bdiff_api.cu — the C ABI declared in include/bdiff.h: handle, weight repacking, topology plan, forward,
 // reverse step.  Host-side logic only; kernels live in bdiff_kernels_fp32.cu / bdiff_edge_tc.cu.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/bdiff.h"
@@ -57,7 +59,9 @@ struct bdiff_handle {
   // plan
   bool have_plan = false;
   Plan plan{};
-  DevBuf plan_buf, rc_buf;
+  DevBuf plan_buf, rc_buf, layers_dev, sched_buf, items_buf;
+  LayerSched sched{};
+  bool mega = true;             // tensor mode: all layers in one persistent kernel (BDIFF_MEGA=0 -> one kernel per pass)
   int Npad = 0;
   long long Epad = 0;
 
@@ -332,6 +336,8 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
     }
     e = tc_configure();
     if (e == cudaSuccess) e = tc_node_configure();
+    if (e == cudaSuccess) e = tc_layers_configure();
+    { const char* m = getenv("BDIFF_MEGA"); h->mega = !(m && m[0] == '0'); }
     h->tc_layer_bytes = tc_blob_bytes(d.Ed, d.Xd);
     h->tc_node_layer_bytes = tc_node_blob_bytes();
     if (e == cudaSuccess) e = h->tc_blob.ensure(h->tc_layer_bytes * d.L);
@@ -350,7 +356,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
 void bdiff_destroy(bdiff_handle* h) {
   if (!h) return;
   if (h->wbuf) cudaFree(h->wbuf);
-  h->plan_buf.release(); h->rc_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
+  h->plan_buf.release(); h->rc_buf.release(); h->layers_dev.release(); h->sched_buf.release(); h->items_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
   delete h;
 }
 
@@ -386,6 +392,10 @@ static void tc_prepare(bdiff_handle* h, cudaStream_t st) {
     unsigned char* nb = static_cast<unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes;
     launch_tc_pack_node(st, h->layers[l], h->layers[last ? l : l + 1], h->embed, h->d, last, nb);
     h->launches += 2;
+  }
+  if (h->layers_dev.ensure(h->layers.size() * sizeof(LayerW)) == cudaSuccess) {
+    cudaMemcpyAsync(h->layers_dev.p, h->layers.data(), h->layers.size() * sizeof(LayerW), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);      // pageable source; runs once per weight update, never inside a graph capture
   }
   h->tc_dirty = false;
 }
@@ -466,8 +476,26 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
       tile_mol[(size_t)t] = k;
     }
   }
+  // dependency tables of the layer megakernel: edge tile -> 32-node tiles of its molecules, node tile -> edge tiles
+  const int ntile32 = (N + 31) / 32;
+  std::vector<int> edge_dep((size_t)2 * (ntile128 + 1), 0), node_dep((size_t)2 * (ntile32 + 1), 0);
+  for (long long t = 0; t < ntile128; ++t) {
+    const long long g1 = std::min<long long>(E, t * 128 + 128) - 1;
+    int k0 = tile_mol[(size_t)t], k1 = k0;
+    while (k1 < B - 1 && edge_off[k1 + 1] <= g1) ++k1;
+    edge_dep[2 * t] = mol_off[k0] / 32;
+    edge_dep[2 * t + 1] = (mol_off[k1 + 1] - 1) / 32;
+  }
+  for (int u = 0; u < ntile32; ++u) {
+    const int n1 = std::min(N, u * 32 + 32) - 1;
+    const int k0 = node_mol[u * 32], k1 = node_mol[n1];
+    const long long e0 = edge_off[k0], e1 = edge_off[k1 + 1] - 1;
+    node_dep[2 * u] = e1 >= e0 ? (int)(e0 / 128) : 0;
+    node_dep[2 * u + 1] = e1 >= e0 ? (int)(e1 / 128) : -1;
+  }
   const size_t o_mo = take((B + 1) * 4), o_ao = take((B + 1) * 4), o_ai = take((M + 1) * 4), o_nm = take(N * 4),
-               o_eo = take((B + 1) * 8), o_tm = take((ntile128 + 1) * 4), o_mk = take(N);
+               o_eo = take((B + 1) * 8), o_tm = take((ntile128 + 1) * 4), o_mk = take(N),
+               o_ed = take((ntile128 + 1) * 8), o_nd = take((ntile32 + 1) * 8);
   std::vector<unsigned char> stage(off, 0);
   memcpy(stage.data() + o_mo, mol_off.data(), (B + 1) * 4);
   memcpy(stage.data() + o_ao, act_off.data(), (B + 1) * 4);
@@ -476,6 +504,8 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   memcpy(stage.data() + o_eo, edge_off.data(), (B + 1) * 8);
   memcpy(stage.data() + o_tm, tile_mol.data(), (size_t)(ntile128 + 1) * 4);
   memcpy(stage.data() + o_mk, mk.data(), N);
+  memcpy(stage.data() + o_ed, edge_dep.data(), edge_dep.size() * 4);
+  memcpy(stage.data() + o_nd, node_dep.data(), node_dep.size() * 4);
   e = h->plan_buf.ensure(off);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->plan_buf.p, stage.data(), off, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -500,6 +530,45 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "plan edge records: %s", cudaGetErrorString(e));
   }
+  h->sched.edge_dep = reinterpret_cast<const int2*>(base + o_ed);
+  h->sched.node_dep = reinterpret_cast<const int2*>(base + o_nd);
+  h->sched.TE = (int)ntile128;
+  h->sched.TN = ntile32;
+  {
+    // Claim order of the layer megakernel.  Virtual time of edge (l, t) = l*TE + t; node (l, u) follows the last edge
+    // tile it reads by `lag` claims (about one wave: by then that tile has normally finished).  Every dependency must
+    // precede its consumer in the list (deadlock freedom), which bounds the lag: edge (l+1, t) reads node (l, u) for
+    // u <= edge_dep[t].y, whose time is l*TE + node_dep[u].y + lag  <  (l+1)*TE + t.
+    const int L = h->d.L, TE = (int)ntile128, TN = ntile32;
+    if (L > 63 || ntile128 >= (1 << 24) || ntile32 >= (1 << 24)) return h->fail(BDIFF_EINVAL, "problem too large for the tile scheduler");
+    long long lag = h->num_sms;
+    for (int t = 0; t < TE; ++t) {
+      const int uh = edge_dep[2 * t + 1];
+      const int th = uh < TN ? node_dep[2 * uh + 1] : -1;
+      if (th >= 0) lag = std::min<long long>(lag, (long long)TE - 1 - (th - t));
+    }
+    if (lag < 0) lag = 0;
+    std::vector<std::pair<long long, int>> order;
+    order.reserve((size_t)L * (TE + TN));
+    for (int l = 0; l < L; ++l) {
+      for (int t = 0; t < TE; ++t) order.emplace_back(2 * ((long long)l * TE + t), (0 << 30) | (l << 24) | t);
+      for (int u = 0; u < TN; ++u) {
+        const int th = node_dep[2 * u + 1];       // -1: no edges at all -> right at the start of the layer
+        const long long tau = (long long)l * TE + (th >= 0 ? th + lag : 0);
+        order.emplace_back(2 * tau + 1, (1 << 30) | (l << 24) | u);
+      }
+    }
+    std::stable_sort(order.begin(), order.end(), [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first < b.first; });
+    std::vector<int> items(order.size());
+    for (size_t i = 0; i < order.size(); ++i) items[i] = order[i].second;
+    e = h->items_buf.ensure(std::max<size_t>(items.size(), 1) * sizeof(int));
+    if (e == cudaSuccess && !items.empty())
+      e = cudaMemcpy(h->items_buf.p, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "scheduler work list: %s", cudaGetErrorString(e));
+    h->sched.items = static_cast<const int*>(h->items_buf.p);
+  }
+  e = h->sched_buf.ensure((2 + (size_t)h->d.L * (size_t)(ntile128 + ntile32)) * sizeof(int));
+  if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "scheduler buffer: %s", cudaGetErrorString(e));
   h->Npad = round_up(N, 128);
   h->Epad = (E + 127) / 128 * 128 + 128;
   e = ensure_work(h);
@@ -547,7 +616,24 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
   launch_node_embed(st, p, d, h->embed, h->layers[0], w);
   mark();
   h->launches += 4;
-  for (int l = 0; l < d.L; ++l) {
+  const bool fused = tensor && h->mega;
+  if (fused) {
+    // all L layers in one persistent kernel (bdiff_layers_tc.cu); its queue head + completion flags are zeroed first
+    LayerSched& q = h->sched;
+    const size_t nsched = 2 + (size_t)d.L * (q.TE + q.TN);      // buffer sized in bdiff_plan_topology
+    q.layers = static_cast<const LayerW*>(h->layers_dev.p);
+    q.edge_blob = static_cast<const unsigned char*>(h->tc_blob.p);
+    q.edge_blob_stride = h->tc_layer_bytes;
+    q.node_blob = static_cast<const unsigned char*>(h->tc_node_blob.p);
+    q.node_blob_stride = h->tc_node_layer_bytes;
+    q.L = d.L;
+    q.sched = static_cast<int*>(h->sched_buf.p);
+    cudaMemsetAsync(q.sched, 0, nsched * sizeof(int), st);
+    launch_layers_tc(st, p, d, h->embed, q, w, h->num_sms);
+    mark();
+    h->launches += 1;
+  }
+  for (int l = 0; l < d.L && !fused; ++l) {
     if (tensor)
       launch_edge_message_tc(st, p, d, h->layers[l],
                              static_cast<const unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes, w, h->num_sms);
@@ -579,15 +665,27 @@ int32_t bdiff_profile_forward(bdiff_handle* h, void* stream, const float* xh, co
   int32_t rc = forward_impl(h, st, xh, t, nullptr, nullptr, context, net_out, &ev);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == BDIFF_OK && e != cudaSuccess) rc = h->fail(BDIFF_ECUDA, "profile sync: %s", cudaGetErrorString(e));
+  if (rc == BDIFF_OK && h->cfg.mode == BDIFF_MODE_TENSOR && h->mega && h->sched_buf.p) {
+    int flag = 0;
+    cudaMemcpy(&flag, static_cast<int*>(h->sched_buf.p) + 1, sizeof(int), cudaMemcpyDeviceToHost);
+    if (flag) rc = h->fail(BDIFF_ECUDA, "layer megakernel: a tile dependency wait timed out");
+  }
   for (int i = 0; i < 8; ++i) ms_host[i] = 0.f;
   if (rc == BDIFF_OK) {
     auto dt = [&](size_t a, size_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, ev[a], ev[b]); return ms; };
     const int L = h->d.L;
     ms_host[0] = dt(0, 1); ms_host[1] = dt(1, 2); ms_host[2] = dt(2, 3);
-    for (int l = 0; l < L; ++l) { ms_host[3] += dt(3 + 2 * l, 4 + 2 * l); ms_host[4] += dt(4 + 2 * l, 5 + 2 * l); }
-    ms_host[5] = dt(3 + 2 * L, 4 + 2 * L);
-    ms_host[6] = dt(0, 4 + 2 * L);
-    ms_host[7] = (float)L;
+    if (ev.size() == 6) {          // fused layers: [prep | edge_embed | node_embed | k_layers_tc | finalize]
+      ms_host[3] = dt(3, 4);       // reported in the edge_message slot; ms_host[7] < 0 marks the fusion
+      ms_host[5] = dt(4, 5);
+      ms_host[6] = dt(0, 5);
+      ms_host[7] = -(float)L;
+    } else {
+      for (int l = 0; l < L; ++l) { ms_host[3] += dt(3 + 2 * l, 4 + 2 * l); ms_host[4] += dt(4 + 2 * l, 5 + 2 * l); }
+      ms_host[5] = dt(3 + 2 * L, 4 + 2 * L);
+      ms_host[6] = dt(0, 4 + 2 * L);
+      ms_host[7] = (float)L;
+    }
   }
   for (cudaEvent_t x : ev) cudaEventDestroy(x);
   return rc;

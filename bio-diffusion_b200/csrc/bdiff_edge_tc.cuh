@@ -25,7 +25,7 @@ __host__ __device__ inline int tc_nc0(int Ed, int Xd) {          // weight chunk
 // kernel's shared-memory tail so that the layer megakernel can overlay the edge and node tails.
 struct TcBars {
   uint64_t full[2], empty[2], a_ready, d_full, wbar, u_free;
-  uint64_t item_full[2], item_empty[2];
+  uint64_t item_full[2], item_empty[2], tile_done;
   int item[2][4];          // megakernel work items {type, layer, tile, -}
   uint32_t tmem_ptr;
   uint32_t pad_;

@@ -66,6 +66,22 @@ void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, co
                          unsigned char* blob);
 void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
                            const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
+// all layers in one persistent kernel (bdiff_layers_tc.cu)
+struct LayerSched {
+  const LayerW* layers;            // [L] device copy of the per-layer weight pointer tables
+  const unsigned char* edge_blob;  // per-layer bf16 blobs of the edge / node passes
+  size_t edge_blob_stride;
+  const unsigned char* node_blob;
+  size_t node_blob_stride;
+  int L, TE, TN;                   // layers, 128-edge tiles, 32-node tiles
+  int* sched;                      // [0] queue head, [1] error flag, [2 + l*(TE+TN) + i] completion flags; zeroed per forward
+  const int2* edge_dep;            // [TE] inclusive range of 32-node tiles whose previous-layer output an edge tile reads
+  const int2* node_dep;            // [TN] inclusive range of edge tiles whose messages a node tile reads
+  const int* items;                // [L*(TE+TN)] work list in claim order: type<<30 | layer<<24 | tile (see bdiff_plan_topology)
+};
+cudaError_t tc_layers_configure();
+void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerSched& q,
+                      const Work& w, int num_sms);
 void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
 
 }  // namespace bdiff

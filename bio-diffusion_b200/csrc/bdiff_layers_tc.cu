@@ -1,0 +1,301 @@
+// bdiff_layers_tc.cu — all L interaction layers of one denoiser forward in ONE persistent tensor-core kernel.
+//
+// Why: with one kernel per pass the forward is quantised twice per layer — 361 edge tiles on 148 SMs are three
+// rounds (19 % of the SM time idle in the last one at the BASELINE batch) and the node pass has work for only 76
+// SMs — and pays ~18 launch / prologue / pipeline-ramp gaps.  Nothing in the network couples molecules inside a
+// layer (gcpnet.py:676-737, 893-930: messages, aggregation and node updates are per molecule), so layer l+1 of
+// a molecule only needs layer l of the same molecule.  This kernel therefore runs the per-tile bodies of
+// k_edge_message_tc and k_node_update_r4 (the very same code, textually included) from a global work list
+//     for l in 0..L-1:  edge tiles (l, 0..TE-1) in order, node tile (l, u) inserted ~one wave of claims after the last
+//                       edge tile it depends on (so its wait is short and the CTA that claims it does not idle)
+// claimed with one atomicAdd per item, with per-tile completion flags as dependencies:
+//     edge (l, t)  waits for node (l-1, u) of every 32-node tile u that intersects the molecules of edge tile t;
+//     node (l, u)  waits for edge (l, t) of every edge tile t that intersects the molecules of node tile u.
+// Every dependency has a smaller queue index and all CTAs are resident (grid <= #SMs, 1 CTA/SM), so the smallest
+// unfinished item can always run: no deadlock.  Spins are bounded (~1 s) and raise sched[1] instead of hanging.
+// Flags are released with fence + st.release after a CTA barrier and acquired with ld.acquire + a gpu-scope fence
+// in every consumer thread (mutable activations are re-read from L2, not from a stale L1 line).
+//
+// Warp roles as in the per-pass kernels; the TMA-producer lane also claims the items (so the next tile's weights
+// stream while the current tile computes) and hands them to the MMA lane and the 8 compute warps through a
+// two-slot mbarrier ring.
+#include "bdiff_node_tc.cuh"
+
+namespace bdiff {
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+union LayersTail {
+  TcBars bars;
+  TcSmemTail edge;
+  NodeR4Tail node;
+};
+constexpr size_t LAYERS_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)RING_STAGE + sizeof(LayersTail) + 1024;
+static_assert(LAYERS_SMEM_BYTES <= 232448, "shared memory budget of the layer megakernel");
+
+template <int ED, int XD>
+__global__ void __launch_bounds__(TC_THREADS2, 1) k_layers_tc(Plan p, Dims d, EmbedW ew, LayerSched q, Work w) {
+  constexpr int HID0 = (64 + XD) / 4;
+  constexpr int H2 = HID0 / 2;
+  constexpr int K0RAW = ED + HID0 + 9;
+  constexpr int K0S = (K0RAW + 15) / 16;
+  constexpr int NC0 = (K0S + 3) / 4;
+  constexpr int NSTRIDE = RING_STAGE;       // node-pass weight chunks use the edge pass's (larger) ring stages here
+  static_assert(HID0 % 2 == 0 && H2 * 3 <= 32 && HID0 + 9 <= 32 && ED % 16 == 0, "layout");
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* X = smem;
+  unsigned char* ring = smem + 5 * X_BLOCK;
+  unsigned char* tail = ring + 2 * RING_STAGE;
+  TcBars& B = *reinterpret_cast<TcBars*>(tail);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int hid0 = d.hid0;
+  const int per_layer = q.TE + q.TN;
+  const int total_items = q.L * per_layer;
+  int* const flags = q.sched + 2;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B.full[i], 1); mbar_init(&B.empty[i], 1);
+      mbar_init(&B.item_full[i], 1); mbar_init(&B.item_empty[i], TC_EPI + 1);
+    }
+    mbar_init(&B.tile_done, TC_EPI);
+    mbar_init(&B.a_ready, TC_EPI);
+    mbar_init(&B.d_full, 1);
+    mbar_init(&B.wbar, 1);
+    mbar_init(&B.u_free, TC_EPI);
+    mbar_fence_init();
+  }
+  if (warp == 8) tmem_alloc(&B.tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = B.tmem_ptr;
+
+  if (warp == 8) {
+    // ============================================================ scheduler + TMA producer (one lane)
+    if (lane == 0) {
+      TcBars& T = B;
+      uint32_t ci = 0;
+      for (uint32_t k = 0;; ++k) {
+        const uint32_t slot = k & 1;
+        mbar_wait_backoff(&B.item_empty[slot], ((k >> 1) & 1) ^ 1);
+        const int qi = atomicAdd(q.sched, 1);
+        int type = -1, layer = 0, tile = 0;
+        if (qi < total_items) {
+          const int it = __ldg(q.items + qi);
+          type = (it >> 30) & 1; layer = (it >> 24) & 63; tile = it & 0xffffff;
+        }
+        B.item[slot][0] = type; B.item[slot][1] = layer; B.item[slot][2] = tile;
+        mbar_arrive(&B.item_full[slot]);
+        if (type < 0) break;
+        if (type == 0) {
+          const unsigned char* blob = q.edge_blob + (size_t)layer * q.edge_blob_stride;
+#include "edge_tile_producer.inc"
+        } else {
+          const int last = layer == q.L - 1;
+          const unsigned char* blob = q.node_blob + (size_t)layer * q.node_blob_stride;
+#include "node_r4_tile_producer.inc"
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ======================================================================= MMA issuer (one lane)
+    if (lane == 0) {
+      TcBars& T = B;
+      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
+                     i32n = umma_idesc_bf16(32, true);
+      const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
+      uint32_t ci = 0, pa = 0, pu = 0;
+      int ms = 28;
+      auto wait_a = [&]() { mbar_wait_backoff(&B.a_ready, pa); pa ^= 1; tc_fence_after(); };
+      auto wait_w = [&]() -> uint32_t {
+        const uint32_t s = ci & 1;
+        mbar_wait_backoff(&B.full[s], (ci >> 1) & 1);
+        tc_fence_after();
+        return raddr + s * RING_STAGE;
+      };
+      auto done_w = [&]() { umma_commit(&B.empty[ci & 1]); ++ci; };
+      auto commit_d = [&]() { umma_commit(&B.d_full); };
+      auto gemm256 = [&](bool fresh, uint32_t dcol = NM_S) {
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t wb = wait_w();
+          for (int s = 0; s < 4; ++s)
+            umma_bf16(tmem + dcol, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256,
+                      fresh ? (j | s) > 0 : true);
+          done_w();
+        }
+      };
+      auto gemm288 = [&](bool fresh_s, bool negate_u) {
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t wb = wait_w();
+          for (int s = 0; s < 4; ++s) {
+            const uint64_t ad = umma_desc_sw128(xaddr + j * X_BLOCK + s * 32);
+            umma_bf16(tmem + NM_S, ad, umma_desc_sw128(wb + s * 32), i256, fresh_s ? (j | s) > 0 : true);
+            umma_bf16(tmem + NM_U, ad, umma_desc_sw128(wb + 256 * 128 + s * 32), negate_u ? i32n : i32,
+                      negate_u ? (j | s) > 0 : true);
+          }
+          done_w();
+        }
+      };
+      auto gemm_extra = [&]() {
+        const uint32_t wb = wait_w();
+        for (int s = 0; s < 2; ++s)
+          umma_bf16(tmem + NM_S, umma_desc_sw128(xaddr + 4 * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256, true);
+        done_w();
+      };
+      (void)ms;
+      for (uint32_t k = 0;; ++k) {
+        const uint32_t slot = k & 1;
+        mbar_wait_backoff(&B.item_full[slot], (k >> 1) & 1);
+        const int type = B.item[slot][0], layer = B.item[slot][1], tile = B.item[slot][2];
+        if (type < 0) break;
+        if (type == 0) {
+#include "edge_tile_mma.inc"
+        } else {
+          const int last = layer == q.L - 1;
+#include "node_r4_tile_mma.inc"
+        }
+        mbar_wait_backoff(&B.tile_done, k & 1);
+        __threadfence();
+        st_release_gpu(flags + (size_t)layer * per_layer + (type == 0 ? tile : q.TE + tile), 1);
+        mbar_arrive(&B.item_empty[slot]);
+      }
+    }
+  } else {
+    // ============================================================================ compute / epilogue warps
+    uint32_t pd = 0, pw = 0;
+    int es = 64;                 // the per-tile bodies' own stamps are off here; this kernel stamps per item (below)
+    int cur_type = -1, cur_layer = -1;
+    auto wait_d = [&]() { mbar_wait(&B.d_full, pd); pd ^= 1; tc_fence_after(); };
+    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&B.a_ready); };
+    (void)es;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t slot = k & 1;
+      mbar_wait(&B.item_full[slot], (k >> 1) & 1);
+      const int type = B.item[slot][0], layer = B.item[slot][1], tile = B.item[slot][2];
+      if (type < 0) break;
+      if (tid == 0 && w.dbg && k < 16) {      // BDIFF_TIMING: {item code, t_fetch, t_start, t_end} for the first 16 items
+        w.dbg[(size_t)blockIdx.x * 64 + 4 * k] = (type << 30) | (layer << 24) | tile;
+        w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 1] = clock64();
+      }
+      // ---- small (vector-channel) weights of this (pass, layer): reload only when they change
+      if (type != cur_type || layer != cur_layer) {
+        named_bar_sync(3, TC_EPI);             // everybody is done with the previous set
+        if (tid == 0) {
+          const LayerW lw = q.layers[layer];       // by value: the pointer loads go out together, not one per copy
+          if (type == 0) {
+            SmallW& s = reinterpret_cast<TcSmemTail*>(tail)->sw;
+            mbar_expect_tx(&B.wbar, sz(XD * HID0) + sz(XD * 3) + sz(HID0 * 32) +
+                                        3 * (sz(256) + sz(256) + sz(256) + sz(96) + sz(32)) + sz(32) + sz(256) + sz(1));
+            auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &B.wbar); };
+            cp(s.Wd0x, lw.Wd0x, XD * HID0); cp(s.Wf0x, lw.Wf0x, XD * 3); cp(s.Wu0, lw.Wu0, HID0 * 32);
+            for (int kk = 0; kk < 3; ++kk) {
+              cp(s.Wdk[kk], lw.Wdk[kk], 256); cp(s.Wuk[kk], lw.Wuk[kk], 256); cp(s.bk[kk], lw.bk[kk], 256);
+              cp(s.Wfk[kk], lw.Wfk[kk], 96); cp(s.bg[kk + 1], lw.bgk[kk], 32);
+            }
+            cp(s.bg[0], lw.bg0, 32); cp(s.wa, lw.wa, 256); cp(s.ba, lw.ba, 1);
+          } else {
+            const int last = layer == q.L - 1;
+            const LayerW wn = q.layers[last ? layer : layer + 1];
+            SmallWR4& s = reinterpret_cast<NodeR4Tail*>(tail)->sw;
+            uint32_t total = sz(1024) + sz(192) + sz(512) + sz(32) + 2 * sz(256) + sz(256) + sz(96) + sz(8) + 2 * sz(256) + sz(1);
+            total += last ? sz(1024) + sz(96) + sz(d.Hin) : sz(256) + 2 * sz(32 * hid0) + 2 * sz(96);
+            mbar_expect_tx(&B.wbar, total);
+            auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &B.wbar); };
+            cp(s.Wdf, lw.Wdf, 64 * 16); cp(s.Wff, lw.Wff, 64 * 3); cp(s.Wuf, lw.Wuf, 16 * 32); cp(s.bgf, lw.bgf, 32);
+            cp(s.b1, lw.b1, 256); cp(s.b2, lw.b2, 256);
+            cp(s.Wdp, lw.Wdp, 32 * 8); cp(s.Wfp, lw.Wfp, 32 * 3); cp(s.Wup, lw.Wup, 8); cp(s.bp, lw.bp, 256);
+            cp(s.wgp, lw.Wgp, 256); cp(s.bgp, lw.bgp, 1);
+            if (!last) {
+              cp(s.u.nx.b0, wn.b0, 256);
+              cp(s.u.nx.Wd0i, wn.Wd0i, 32 * hid0); cp(s.u.nx.Wd0j, wn.Wd0j, 32 * hid0);
+              cp(s.u.nx.Wf0i, wn.Wf0i, 96); cp(s.u.nx.Wf0j, wn.Wf0j, 96);
+            } else {
+              cp(s.u.pj.pWd, ew.pWd, 32 * 32); cp(s.u.pj.pWf, ew.pWf, 96); cp(s.u.pj.pbs, ew.pbs, d.Hin);
+            }
+          }
+        }
+        mbar_wait(&B.wbar, pw);
+        pw ^= 1;
+        cur_type = type; cur_layer = layer;
+      }
+      // ---- dependencies: completion flags of the producer tiles (bounded spin), then a gpu-scope acquire in
+      //      every thread before it reads activations written by other SMs
+      if (tid == 0) {
+        int lo = 0, hi = -1;
+        const int* fbase = flags;
+        if (type == 0) {
+          if (layer > 0) {
+            const int2 dep = q.edge_dep[tile];
+            lo = dep.x; hi = dep.y;
+            fbase = flags + (size_t)(layer - 1) * per_layer + q.TE;
+          }
+        } else {
+          const int2 dep = q.node_dep[tile];
+          lo = dep.x; hi = dep.y;
+          fbase = flags + (size_t)layer * per_layer;
+        }
+        const long long t0 = clock64();
+        for (int u = lo; u <= hi; ++u) {
+          while (ld_acquire_gpu(fbase + u) == 0) {
+            if (clock64() - t0 > (1ll << 31)) { atomicExch(q.sched + 1, 1); break; }
+          }
+        }
+      }
+      named_bar_sync(3, TC_EPI);
+      __threadfence();
+      if (tid == 0 && w.dbg && k < 16) w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 2] = clock64();
+      if (type == 0) {
+        TcSmemTail& T = *reinterpret_cast<TcSmemTail*>(tail);
+        const int half = tid >> 7, r = tid & 127;
+        const SmallW& sw = T.sw;
+        float* exch_mine = &T.sT[half][r][0];
+        const float* exch_other = &T.sT[half ^ 1][r][0];
+#include "edge_tile_epilogue.inc"
+      } else {
+        NodeR4Tail& T = *reinterpret_cast<NodeR4Tail*>(tail);
+        const int last = layer == q.L - 1;
+        const int l = lane, s = warp, c0 = warp * 32;
+        const SmallWR4& sw = T.sw;
+#include "node_r4_tile_epilogue.inc"
+      }
+      // ---- completion: every compute thread arrives (release) on tile_done after its last global write; the MMA
+      //      lane — idle at this point — acquires it, makes the writes visible gpu-wide and raises the flag, so the
+      //      ~1 us fence is off the compute warps' critical path
+      if (tid == 0 && w.dbg && k < 16) w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 3] = clock64();
+      mbar_arrive(&B.tile_done);
+      mbar_arrive(&B.item_empty[slot]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
+cudaError_t tc_layers_configure() {
+  cudaError_t e = cudaFuncSetAttribute(k_layers_tc<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)LAYERS_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_layers_tc<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAYERS_SMEM_BYTES);
+}
+
+void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerSched& q,
+                      const Work& w, int num_sms) {
+  const int items = q.L * (q.TE + q.TN);
+  const int grid = items < num_sms ? items : num_sms;
+  if (d.Ed == 64) k_layers_tc<64, 16><<<grid, TC_THREADS2, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
+  else k_layers_tc<16, 8><<<grid, TC_THREADS2, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
+}
+
+}  // namespace bdiff

@@ -43,11 +43,27 @@ def make_net(cname, seed, mode, scale=1.0):
     return net.cuda(), ocfg, sd
 
 
-@pytest.mark.parametrize("node_r4", ["0", "1"])     # 128-node-tile kernel / row-replicated 32-node-tile kernel
+VARIANTS = {            # BDIFF_MEGA, BDIFF_NODE_R4
+    "layers_fused": ("1", None),      # default: all layers in one persistent kernel (k_layers_tc)
+    "split_r4": ("0", "1"),           # one kernel per pass, row-replicated 32-node-tile node kernel
+    "split_128": ("0", "0"),          # one kernel per pass, 128-node-tile node kernel
+}
+
+
+def set_variant(monkeypatch, variant):
+    mega, r4 = VARIANTS[variant]
+    monkeypatch.setenv("BDIFF_MEGA", mega)
+    if r4 is None:
+        monkeypatch.delenv("BDIFF_NODE_R4", raising=False)
+    else:
+        monkeypatch.setenv("BDIFF_NODE_R4", r4)
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("name", ["qm9_small_masked", "qm9_tiny_sizes", "qm9_b4_n19", "qm9_cond", "geom_mixed",
                                   "geom_max181"])
-def test_tensor_forward_close_to_reference(name, node_r4, monkeypatch):
-    monkeypatch.setenv("BDIFF_NODE_R4", node_r4)
+def test_tensor_forward_close_to_reference(name, variant, monkeypatch):
+    set_variant(monkeypatch, variant)
     fx = load_golden(name)
     net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], "tensor")
     ctx = fx["context"].cuda() if fx["context"] is not None else None
@@ -61,14 +77,13 @@ def test_tensor_forward_close_to_reference(name, node_r4, monkeypatch):
     assert max_abs <= 2e-2 * scale and rms <= 5e-3 * scale
 
 
-@pytest.mark.parametrize("b,node_r4", [(128, None), (128, "0"), (300, "1"), (300, None)])
-def test_tensor_and_parity_modes_agree_full_size(b, node_r4, monkeypatch):
-    """QM9 B=128 (BASELINE config) and B=300 (more 32-node tiles than SMs: persistent loop of the row-replicated node
-    kernel when forced, 128-node tiles by default): tensor mode vs parity mode on the same input, both on the GPU."""
-    if node_r4 is not None:
-        monkeypatch.setenv("BDIFF_NODE_R4", node_r4)
-    else:
-        monkeypatch.delenv("BDIFF_NODE_R4", raising=False)
+@pytest.mark.parametrize("b,variant", [(128, "layers_fused"), (128, "split_r4"), (128, "split_128"),
+                                       (300, "layers_fused"), (300, "split_r4"), (300, "split_128")])
+def test_tensor_and_parity_modes_agree_full_size(b, variant, monkeypatch):
+    """QM9 B=128 (BASELINE config) and B=300 (more 32-node tiles than SMs): tensor mode, every kernel variant, vs parity
+    mode on the same input, both on the GPU.  The fused variant goes through bdiff_profile_forward once as well, which
+    fails if a dependency wait of the megakernel ever timed out."""
+    set_variant(monkeypatch, variant)
     g = torch.Generator().manual_seed(4)
     nat = 19
     n = b * nat
@@ -82,6 +97,11 @@ def test_tensor_and_parity_modes_agree_full_size(b, node_r4, monkeypatch):
     for mode in ("parity", "tensor"):
         net, _, _ = make_net("qm9", 7, mode)
         outs[mode] = net.denoise(bi, mask, xh, t)
+        if mode == "tensor":
+            prof, out2 = net.profile_forward(bi, mask, xh, t)
+            assert ("layers_fused" in prof) == (variant == "layers_fused")
+            # two runs differ at the bf16-rounding level: the aggregation uses floating-point atomics (any order)
+            assert (out2 - outs[mode]).abs().max().item() <= 1e-2 * max(1.0, outs[mode].abs().max().item())
     d = (outs["tensor"] - outs["parity"])
     scale = max(1.0, outs["parity"].abs().max().item())
     print(f"full-size tensor vs parity: max {d.abs().max().item():.3e} rms {d.pow(2).mean().sqrt().item():.3e}")
