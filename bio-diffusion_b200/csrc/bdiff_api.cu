@@ -77,6 +77,8 @@ struct bdiff_handle {
   size_t tc_layer_bytes = 0, tc_node_layer_bytes = 0;
   bool tc_dirty = true;
   int num_sms = 148;
+  cudaStream_t side = nullptr;          // fork/join stream: the edge embedding runs next to the node embedding
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -326,6 +328,11 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
     gcp_names(h->seen, p + "node_position_update_gcp.", false, true);
   }
   h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    h->side = nullptr;               // fall back to a single stream
+  }
   cudaError_t e = configure_kernels();
   if (e == cudaSuccess && cfg->mode == BDIFF_MODE_TENSOR) {
     if (!tc_supported(d.Ed, d.Xd)) {
@@ -356,6 +363,9 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
 void bdiff_destroy(bdiff_handle* h) {
   if (!h) return;
   if (h->wbuf) cudaFree(h->wbuf);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   h->plan_buf.release(); h->rc_buf.release(); h->layers_dev.release(); h->sched_buf.release(); h->items_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
   delete h;
 }
@@ -611,9 +621,21 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
   mark();
   launch_prep(st, p, d, xh, t_nodes, coef_table, step_ptr, context, w);
   mark();
-  launch_edge_embed(st, p, d, h->embed, w);
+  // the edge embedding (e, xi, frames) and the node embedding (+ layer-0 endpoint projections) are independent and
+  // neither fills the chip: run them side by side (fork/join through events; also valid under stream capture).
+  // With per-kernel timing marks requested they stay in order on one stream.
+  const bool fork = h->side != nullptr && ev == nullptr;
+  if (fork) {
+    cudaEventRecord(h->ev_fork, st);
+    cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    launch_edge_embed(h->side, p, d, h->embed, w);
+    cudaEventRecord(h->ev_join, h->side);
+  } else {
+    launch_edge_embed(st, p, d, h->embed, w);
+  }
   mark();
   launch_node_embed(st, p, d, h->embed, h->layers[0], w);
+  if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
   mark();
   h->launches += 4;
   const bool fused = tensor && h->mega;
