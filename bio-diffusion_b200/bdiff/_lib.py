@@ -48,6 +48,7 @@ PROTOTYPES = {
     "bdiff_decode_z0": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "bdiff_center_noise": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bdiff_check": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "bdiff_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

@@ -154,6 +154,8 @@ class GCDMSampler:
         if cfg.include_charges:
             h_int = (xh[:, 3 + a:] * cfg.norm_values[2] + cfg.norm_biases[2]) * mf
             parts.append((torch.round(h_int).long() * mask.long().unsqueeze(-1)).float())
+        # deferred device-side conditions of the chain (synchronises; see bdiff_check in include/bdiff.h)
+        _lib.check(h, lib.bdiff_check(h, self.net._stream()), "bdiff_check")
         # CoG drift correction (variational_diffusion.py:1391-1402) — the single host sync of the chain
         tot = torch.zeros((b, 3), device=dev).index_add_(0, batch_index, x)
         if tot.abs().max().item() > 5e-2:

@@ -577,8 +577,14 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
     if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "scheduler work list: %s", cudaGetErrorString(e));
     h->sched.items = static_cast<const int*>(h->items_buf.p);
   }
-  e = h->sched_buf.ensure((2 + (size_t)h->d.L * (size_t)(ntile128 + ntile32)) * sizeof(int));
-  if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "scheduler buffer: %s", cudaGetErrorString(e));
+  {
+    const size_t nsched = 2 + (size_t)h->d.L * (size_t)(ntile128 + ntile32);
+    e = h->sched_buf.ensure((nsched + 1) * sizeof(int));
+    if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "scheduler buffer: %s", cudaGetErrorString(e));
+    h->sched.sched = static_cast<int*>(h->sched_buf.p);
+    h->sched.err = h->sched.sched + nsched;
+    cudaMemset(h->sched.err, 0, sizeof(int));
+  }
   h->Npad = round_up(N, 128);
   h->Epad = (E + 127) / 128 * 128 + 128;
   e = ensure_work(h);
@@ -649,7 +655,6 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
     q.node_blob = static_cast<const unsigned char*>(h->tc_node_blob.p);
     q.node_blob_stride = h->tc_node_layer_bytes;
     q.L = d.L;
-    q.sched = static_cast<int*>(h->sched_buf.p);
     cudaMemsetAsync(q.sched, 0, nsched * sizeof(int), st);
     launch_layers_tc(st, p, d, h->embed, q, w, h->num_sms);
     mark();
@@ -689,8 +694,8 @@ int32_t bdiff_profile_forward(bdiff_handle* h, void* stream, const float* xh, co
   if (rc == BDIFF_OK && e != cudaSuccess) rc = h->fail(BDIFF_ECUDA, "profile sync: %s", cudaGetErrorString(e));
   if (rc == BDIFF_OK && h->cfg.mode == BDIFF_MODE_TENSOR && h->mega && h->sched_buf.p) {
     int flag = 0;
-    cudaMemcpy(&flag, static_cast<int*>(h->sched_buf.p) + 1, sizeof(int), cudaMemcpyDeviceToHost);
-    if (flag) rc = h->fail(BDIFF_ECUDA, "layer megakernel: a tile dependency wait timed out");
+    cudaMemcpy(&flag, h->sched.err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (flag) { cudaMemset(h->sched.err, 0, sizeof(int)); rc = h->fail(BDIFF_ECUDA, "layer megakernel: a tile dependency wait timed out"); }
   }
   for (int i = 0; i < 8; ++i) ms_host[i] = 0.f;
   if (rc == BDIFF_OK) {
@@ -778,6 +783,19 @@ int32_t bdiff_center_noise(bdiff_handle* h, void* stream, const float* noise_x, 
   h->launches++;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "center_noise: %s", cudaGetErrorString(e));
+}
+
+int32_t bdiff_check(bdiff_handle* h, void* stream) {
+  if (!h) return BDIFF_EINVAL;
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "check: %s", cudaGetErrorString(e));
+  if (h->cfg.mode == BDIFF_MODE_TENSOR && h->mega && h->sched_buf.p && h->have_plan) {
+    int flag = 0;
+    e = cudaMemcpy(&flag, h->sched.err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "check: %s", cudaGetErrorString(e));
+    if (flag) { cudaMemset(h->sched.err, 0, sizeof(int)); return h->fail(BDIFF_ECUDA, "layer megakernel: a tile dependency wait timed out"); }
+  }
+  return BDIFF_OK;
 }
 
 int64_t bdiff_launch_count(const bdiff_handle* h) { return h ? h->launches : 0; }

@@ -12,7 +12,7 @@
 //     edge (l, t)  waits for node (l-1, u) of every 32-node tile u that intersects the molecules of edge tile t;
 //     node (l, u)  waits for edge (l, t) of every edge tile t that intersects the molecules of node tile u.
 // Every dependency has a smaller queue index and all CTAs are resident (grid <= #SMs, 1 CTA/SM), so the smallest
-// unfinished item can always run: no deadlock.  Spins are bounded (~1 s) and raise sched[1] instead of hanging.
+// unfinished item can always run: no deadlock.  Spins are bounded (~1 s) and raise a sticky error word (bdiff_check) instead of hanging.
 // Flags are released with fence + st.release after a CTA barrier and acquired with ld.acquire + a gpu-scope fence
 // in every consumer thread (mutable activations are re-read from L2, not from a stale L1 line).
 //
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) k_layers_tc(Plan p, Dims d, Em
         const long long t0 = clock64();
         for (int u = lo; u <= hi; ++u) {
           while (ld_acquire_gpu(fbase + u) == 0) {
-            if (clock64() - t0 > (1ll << 31)) { atomicExch(q.sched + 1, 1); break; }
+            if (clock64() - t0 > (1ll << 31)) { atomicExch(q.err, 1); break; }
           }
         }
       }

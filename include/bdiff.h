@@ -142,6 +142,12 @@ BDIFF_API int32_t bdiff_decode_z0(bdiff_handle* h, void* stream, const float* z0
 BDIFF_API int32_t bdiff_center_noise(bdiff_handle* h, void* stream, const float* noise_x, const float* noise_h,
                                      float* z);
 
+/* Synchronises `stream` and reports deferred device-side conditions of the work issued so far on this handle.
+ * Today: the tile scheduler of the all-layers tensor-core kernel (replaces the kernel boundaries between
+ * GCPInteractions layers, gcpnet.py:1161-1176) raises a flag if a dependency wait ever times out; that is an internal
+ * error (BDIFF_ECUDA), never expected.  Call after a chain of bdiff_reverse_step / before trusting a result. */
+BDIFF_API int32_t bdiff_check(bdiff_handle* h, void* stream);
+
 /* Counters for bench.py: kernels launched by this handle since creation. */
 BDIFF_API int64_t bdiff_launch_count(const bdiff_handle* h);
 
