@@ -49,6 +49,9 @@ PROTOTYPES = {
                                     C.c_void_p, C.c_void_p]),
     "bdiff_center_noise": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bdiff_check": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "bdiff_optimizer_chunk": (C.c_int32, []),
+    "bdiff_optimizer_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
     "bdiff_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

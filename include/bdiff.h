@@ -148,6 +148,42 @@ BDIFF_API int32_t bdiff_center_noise(bdiff_handle* h, void* stream, const float*
  * error (BDIFF_ECUDA), never expected.  Call after a chain of bdiff_reverse_step / before trusting a result. */
 BDIFF_API int32_t bdiff_check(bdiff_handle* h, void* stream);
 
+/* ---- optimiser side of a training step: adaptive gradient-norm clipping + AdamW(amsgrad) + EMA --
+ * Replaces, per step: get_grad_norm + Queue statistics + clip_gradients (qm9_mol_gen_ddpm.py:1267-1304,
+ * src/models/__init__.py:90-113,442-466), torch.optim.AdamW(lr 1e-4, weight_decay 1e-12, amsgrad) (configs/model/
+ * *_mol_gen_ddpm.yaml:3-8) and the EMA callback (src/utils/__init__.py:125-142) by three multi-tensor kernels with
+ * no host synchronisation.  All pointers are device pointers owned by the caller.
+ *   tensors_dev       one record per parameter tensor (max_exp_avg_sq / ema may be NULL)
+ *   chunk_*_dev       the tensors cut into chunks of bdiff_optimizer_chunk() elements: chunk c covers elements
+ *                     [chunk_start[c], chunk_start[c] + chunk) of tensor chunk_tensor[c]
+ *   partial_dev       scratch, num_chunks doubles
+ *   state_dev         BDIFF_OPT_STATE_WORDS 32-bit words, zero-initialised once by the caller and then owned by the
+ *                     library: [0] step count (int), [1] history length (int), [2] ring position (int), [3] last
+ *                     gradient norm (float), [4] last allowed norm (float), [5] last clip coefficient (float),
+ *                     [6] clipped? (int), [8 ...] norm history (floats).  Seed the history like the reference
+ *                     (one entry of 3000.0: state[1] = 1, state[2] = 1 % queue_len, state[8] = 3000.0f). */
+#define BDIFF_OPT_MAX_QUEUE 120
+#define BDIFF_OPT_STATE_WORDS (8 + BDIFF_OPT_MAX_QUEUE)
+typedef struct bdiff_opt_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  float* max_exp_avg_sq;
+  float* ema;
+  int64_t numel;
+} bdiff_opt_tensor;
+typedef struct bdiff_opt_hyper {
+  float lr, beta1, beta2, eps, weight_decay, ema_decay;
+  int32_t amsgrad;     /* 1: keep the running maximum of exp_avg_sq */
+  int32_t clip;        /* 1: clip to 1.5 * mean + 2 * std of the norm history, then push min(norm, limit) */
+  int32_t queue_len;   /* history length (reference: 50) */
+} bdiff_opt_hyper;
+BDIFF_API int32_t bdiff_optimizer_chunk(void);
+BDIFF_API int32_t bdiff_optimizer_step(void* stream, const bdiff_opt_tensor* tensors_dev, const int32_t* chunk_tensor_dev,
+                                       const int64_t* chunk_start_dev, int32_t num_chunks, double* partial_dev,
+                                       int32_t* state_dev, const bdiff_opt_hyper* hyper);
+
 /* Counters for bench.py: kernels launched by this handle since creation. */
 BDIFF_API int64_t bdiff_launch_count(const bdiff_handle* h);
 
