@@ -28,7 +28,12 @@ __global__ void __launch_bounds__(OPT_THREADS) k_opt_sumsq(const bdiff_opt_tenso
   const int64_t n = min((int64_t)OPT_CHUNK, t.numel - s);
   const float* g = t.grad + s;
   float acc = 0.f;
-  for (int64_t i = threadIdx.x; i < n; i += OPT_THREADS) acc = fmaf(g[i], g[i], acc);
+  const int64_t n4 = (((uintptr_t)g & 15) == 0) ? n / 4 : 0;
+  for (int64_t i = threadIdx.x; i < n4; i += OPT_THREADS) {
+    const float4 q = reinterpret_cast<const float4*>(g)[i];
+    acc = fmaf(q.x, q.x, acc); acc = fmaf(q.y, q.y, acc); acc = fmaf(q.z, q.z, acc); acc = fmaf(q.w, q.w, acc);
+  }
+  for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += OPT_THREADS) acc = fmaf(g[i], g[i], acc);
   __shared__ double red[OPT_THREADS];
   red[threadIdx.x] = (double)acc;
   __syncthreads();
@@ -96,19 +101,42 @@ __global__ void __launch_bounds__(OPT_THREADS) k_opt_apply(const bdiff_opt_tenso
   const float* g = t.grad + s;
   float* m = t.exp_avg + s;
   float* v = t.exp_avg_sq + s;
-  float* vm = t.max_exp_avg_sq ? t.max_exp_avg_sq + s : nullptr;
+  float* vm = (hp.amsgrad && t.max_exp_avg_sq) ? t.max_exp_avg_sq + s : nullptr;
   float* e = t.ema ? t.ema + s : nullptr;
-  for (int64_t i = threadIdx.x; i < n; i += OPT_THREADS) {
-    const float gi = g[i] * coef;
-    float pi = p[i] * decay;
-    const float mi = m[i] * hp.beta1 + (1.f - hp.beta1) * gi;
-    float vi = v[i] * hp.beta2 + (1.f - hp.beta2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    if (hp.amsgrad && vm) { vi = fmaxf(vm[i], vi); vm[i] = vi; }
-    const float denom = sqrtf(vi) / bc2s + hp.eps;
+  auto upd = [&](float& pi, float gi, float& mi, float& vi, float* vmi, float* ei) {
+    gi *= coef;
+    pi *= decay;
+    mi = mi * hp.beta1 + (1.f - hp.beta1) * gi;
+    vi = vi * hp.beta2 + (1.f - hp.beta2) * gi * gi;
+    float vv = vi;
+    if (vmi) { vv = fmaxf(*vmi, vi); *vmi = vv; }
+    const float denom = sqrtf(vv) / bc2s + hp.eps;
     pi -= step_size * (mi / denom);
-    p[i] = pi;
-    if (e) { const float ei = e[i]; e[i] = ei - (ei - pi) * (1.f - hp.ema_decay); }
+    if (ei) *ei = *ei - (*ei - pi) * (1.f - hp.ema_decay);
+  };
+  // 16-byte accesses when every array of this chunk is 16-byte aligned (torch allocations are; s is a multiple of 4)
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)vm | (uintptr_t)e) & 15) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  for (int64_t i = threadIdx.x; i < n4; i += OPT_THREADS) {
+    float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    const float4 G = reinterpret_cast<const float4*>(g)[i];
+    float4 VM = vm ? reinterpret_cast<float4*>(vm)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 E = e ? reinterpret_cast<float4*>(e)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    upd(P.x, G.x, M.x, V.x, vm ? &VM.x : nullptr, e ? &E.x : nullptr);
+    upd(P.y, G.y, M.y, V.y, vm ? &VM.y : nullptr, e ? &E.y : nullptr);
+    upd(P.z, G.z, M.z, V.z, vm ? &VM.z : nullptr, e ? &E.z : nullptr);
+    upd(P.w, G.w, M.w, V.w, vm ? &VM.w : nullptr, e ? &E.w : nullptr);
+    reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
+    if (vm) reinterpret_cast<float4*>(vm)[i] = VM;
+    if (e) reinterpret_cast<float4*>(e)[i] = E;
+  }
+  for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += OPT_THREADS) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    float vmi = vm ? vm[i] : 0.f, ei = e ? e[i] : 0.f;
+    upd(pi, g[i], mi, vi, vm ? &vmi : nullptr, e ? &ei : nullptr);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (vm) vm[i] = vmi;
+    if (e) e[i] = ei;
   }
 }
 
