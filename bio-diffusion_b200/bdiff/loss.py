@@ -1,10 +1,12 @@
-"""GCDMEvalNLL — evaluation-mode negative log-likelihood of GCDM with the B200 denoiser (forward only).
+"""GCDMEvalNLL / GCDMTrainLoss — the GCDM objective with the B200 denoiser (forward only).
 
 Replaces EquivariantVariationalDiffusion.forward in eval mode (reference
 src/models/components/variational_diffusion.py:955-1160 with :501-556, :598-699, :702-732, :910-931) and the
 evaluation branch of the Lightning module's assembly (src/models/qm9_mol_gen_ddpm.py:184-262): two denoiser calls
 (t ~ U{1..T} and t = 0) through libbdiff_sm100, the scalar bookkeeping in torch on the same device.
-Backward / training is not implemented (forward only here).
+`GCDMTrainLoss` is the training-mode L2 objective of the same function (one denoiser call, t ~ U{0..T}, L0 selected
+by the t == 0 mask; :979-980,985,1054-1055,1068-1069,1083-1103 and qm9_mol_gen_ddpm.py:232-245) — the VALUE only: the
+backward pass through the denoiser is not implemented.
 """
 from __future__ import annotations
 
@@ -36,7 +38,7 @@ class GCDMEvalNLL:
     @torch.inference_mode()
     def __call__(self, batch_index: torch.Tensor, mask: torch.Tensor, x: torch.Tensor, one_hot: torch.Tensor,
                  charges: torch.Tensor, context: Optional[torch.Tensor] = None, t_int: Optional[torch.Tensor] = None,
-                 noise: Optional[NoiseFn] = None):
+                 noise: Optional[NoiseFn] = None, training: bool = False, norm_training_by_max_nodes: bool = False):
         """x [N,3] (CoG-free), one_hot [N,A], charges [N] (or [N,0] without charges), context [N,C] or None.
         Returns (nll [B], terms dict).  RNG order matches the reference: t_int, then randn(N,3), randn(N,F) twice."""
         cfg = self.cfg
@@ -69,8 +71,10 @@ class GCDMEvalNLL:
         num_nodes = torch.zeros(nmol, dtype=torch.long, device=dev).index_add_(0, batch_index, mask.long())
         sub_d = ((num_nodes - 1) * 3).float()
         delta_log_px = -sub_d * math.log(cfg.norm_values[0])
+        if training:
+            delta_log_px = torch.zeros_like(delta_log_px)
         if t_int is None:
-            t_int = torch.randint(1, T + 1, size=(nmol, 1), device=dev)
+            t_int = torch.randint(0 if training else 1, T + 1, size=(nmol, 1), device=dev)
         t_int = t_int.to(dev)
         s = (t_int - 1) / T
         t = t_int / T
@@ -86,16 +90,23 @@ class GCDMEvalNLL:
         snr_weight = (torch.exp(-(g_s - g_t)) - 1).squeeze(-1)
         g0, g_T = gamma[0], gamma[T]
         neg_log_constants = -(sub_d * (-(0.5 * g0) - 0.5 * math.log(2 * math.pi)))
+        if training:
+            snr_weight = torch.ones_like(error_t)
+            neg_log_constants = torch.zeros_like(neg_log_constants)
         mu_T = alpha(g_T) * xh
         sig_T = sigma(g_T)
         kl = lambda mu2, qs, d: d * torch.log(1.0 / qs) + 0.5 * (d * qs ** 2 + mu2) - 0.5 * d
         kl_prior = kl(seg_sum(mu_T[:, :3] ** 2), sig_T, sub_d) + kl(seg_sum((mu_T[:, 3:] ** 2) * mf[:, None]), sig_T, 1)
-        eps_0 = centered_noise()
-        z_0 = alpha(g0) * xh + sigma(g0) * eps_0
-        net_0 = self.net.denoise(batch_index, mask, z_0, torch.zeros((n, 1), device=dev), context, nmol)
+        if training:      # L0 from the same noised sample, selected by the t == 0 mask below
+            eps_0, z_0, net_0 = eps_t, z_t, net_out
+            sig0 = sigma(g_t)[batch_index]
+        else:
+            eps_0 = centered_noise()
+            z_0 = alpha(g0) * xh + sigma(g0) * eps_0
+            net_0 = self.net.denoise(batch_index, mask, z_0, torch.zeros((n, 1), device=dev), context, nmol)
+            sig0 = sigma(g0)
         loss_0_x = 0.5 * seg_sum((eps_0[:, :3] - net_0[:, :3]) ** 2)
         a = cfg.num_atom_types
-        sig0 = sigma(g0)
         cen = z_0[:, 3:3 + a] * cfg.norm_values[1] + cfg.norm_biases[1] - 1
         onehot_u = h_cat * cfg.norm_values[1] + cfg.norm_biases[1]
         log_prop = torch.log(_cdf((cen + 0.5) / (sig0 * cfg.norm_values[1])) - _cdf((cen - 0.5) / (sig0 * cfg.norm_values[1]))
@@ -111,7 +122,23 @@ class GCDMEvalNLL:
         loss_0_h = -log_ph
         idx = torch.tensor([self.keys.index(int(v)) for v in num_nodes.tolist()], device=dev)
         log_pn = self.log_pn.to(dev)[idx]
-        nll = T * 0.5 * snr_weight * error_t + (loss_0_x + loss_0_h + neg_log_constants) + kl_prior - delta_log_px - log_pn
+        if training:
+            t0 = (t_int == 0).float().squeeze(-1)
+            loss_0_x, loss_0_h, error_t = loss_0_x * t0, loss_0_h * t0, error_t * (1 - t0)
+            eff = (num_nodes.max() if norm_training_by_max_nodes else num_nodes).float()
+            denom = (3 + cfg.num_h) * eff
+            nll = 0.5 * (error_t / denom) + (loss_0_x / denom + loss_0_h) + kl_prior - delta_log_px - log_pn
+        else:
+            nll = T * 0.5 * snr_weight * error_t + (loss_0_x + loss_0_h + neg_log_constants) + kl_prior - delta_log_px - log_pn
         terms = dict(delta_log_px=delta_log_px, error_t=error_t, SNR_weight=snr_weight, loss_0_x=loss_0_x, loss_0_h=loss_0_h,
                      neg_log_constants=neg_log_constants, kl_prior=kl_prior, log_pN=log_pn, t_int=t_int.squeeze(-1))
         return nll, terms
+
+
+class GCDMTrainLoss(GCDMEvalNLL):
+    """Training-mode objective (loss_type "l2"): `loss, terms = GCDMTrainLoss(net, histogram)(batch_index, mask, x, ...)`.
+    Forward value only (inference mode); see the module docstring."""
+
+    def __call__(self, *args, **kwargs):
+        kwargs.setdefault("training", True)
+        return super().__call__(*args, **kwargs)

@@ -498,8 +498,12 @@ def _cdf_std_gaussian(x: torch.Tensor) -> torch.Tensor:
 def eval_nll(sd, cfg: OracleConfig, batch_index: torch.Tensor, mask: torch.Tensor, x: torch.Tensor,
              one_hot: torch.Tensor, charges: torch.Tensor, context: Optional[torch.Tensor],
              n_nodes_hist: Dict[int, int], randn: NoiseFn, t_int: Optional[torch.Tensor] = None,
-             denoise: Optional[Callable] = None):
-    """NLL per molecule in evaluation mode (two denoiser calls) + its terms.
+             denoise: Optional[Callable] = None, training: bool = False, norm_training_by_max_nodes: bool = False):
+    """NLL per molecule in evaluation mode (two denoiser calls) + its terms; with `training=True` the training-mode
+    L2 objective instead (ONE denoiser call; variational_diffusion.py:979-980,985,1054-1055,1068-1069,1083-1103 and the
+    training branch of the Lightning assembly, qm9_mol_gen_ddpm.py:232-245; loss_type "l2" as shipped): t_int ~
+    randint(0, T+1), delta_log_px = 0, SNR weight 1, no constants, L0 from (z_t, eps_t, net_out, gamma_t) masked by
+    t == 0, error_t masked by t != 0, both normalised by (3 + F) * n.
 
     Restates EquivariantVariationalDiffusion.atom_types_and_coords_forward with self.training == False
     (variational_diffusion.py:955-1160: normalize :702-732, compute_noised_representation :910-931,
@@ -524,8 +528,10 @@ def eval_nll(sd, cfg: OracleConfig, batch_index: torch.Tensor, mask: torch.Tenso
     num_nodes = torch.zeros(nmol, dtype=torch.long).index_add_(0, batch_index, mask.long())
     sub_d = ((num_nodes - 1) * 3).float()                                       # subspace_dimensionality :492-498
     delta_log_px = -sub_d * math.log(cfg.norm_values[0])                        # :950-952
+    if training:
+        delta_log_px = torch.zeros_like(delta_log_px)                           # :979-980
     if t_int is None:
-        t_int = torch.randint(1, T + 1, size=(nmol, 1))                         # eval: lowest_t = 1 (:986-991)
+        t_int = torch.randint(0 if training else 1, T + 1, size=(nmol, 1))      # lowest_t (:985-991)
     s_int = t_int - 1
     s, t = s_int / T, t_int / T
     g_s = gamma[torch.round(s * T).long()]                                      # [B,1]
@@ -542,6 +548,9 @@ def eval_nll(sd, cfg: OracleConfig, batch_index: torch.Tensor, mask: torch.Tenso
     snr_weight = (torch.exp(-(g_s - g_t)) - 1).squeeze(-1)                      # :1057-1058
     g0 = gamma[0]
     neg_log_constants = -(sub_d * (-(0.5 * g0) - 0.5 * math.log(2 * math.pi)))  # :579-595,1062-1066
+    if training:
+        snr_weight = torch.ones_like(error_t)                                   # :1054-1055
+        neg_log_constants = torch.zeros_like(neg_log_constants)                 # :1068-1069
     # KL prior (:501-556)
     g_T = gamma[T]
     mu_T = alpha(g_T) * xh
@@ -550,13 +559,18 @@ def eval_nll(sd, cfg: OracleConfig, batch_index: torch.Tensor, mask: torch.Tenso
     kl_x = kl(sum_mol(mu_T[:, :3] ** 2), sig_T, sub_d)
     kl_h = kl(sum_mol((mu_T[:, 3:] ** 2) * mf[:, None]), sig_T, 1)
     kl_prior = kl_x + kl_h
-    # L0 at t = 0 with fresh noise (:1104-1132)
-    eps_0 = combined_noise(randn, cfg, batch_index, mask, nmol)
-    z_0 = alpha(g0) * xh + sigma(g0) * eps_0
-    net_0 = denoise(batch_index, mask, z_0, torch.zeros((xh.shape[0], 1)), ctx)
+    if training:
+        # L0 from the SAME noised sample, as if gamma_t were gamma_0; selected by the t == 0 mask below (:1083-1103)
+        eps_0, z_0, net_0 = eps_t, z_t, net_out
+        sig0 = sigma(g_t)[batch_index]
+    else:
+        # L0 at t = 0 with fresh noise (:1104-1132)
+        eps_0 = combined_noise(randn, cfg, batch_index, mask, nmol)
+        z_0 = alpha(g0) * xh + sigma(g0) * eps_0
+        net_0 = denoise(batch_index, mask, z_0, torch.zeros((xh.shape[0], 1)), ctx)
+        sig0 = sigma(g0)
     loss_0_x = 0.5 * sum_mol((eps_0[:, :3] - net_0[:, :3]) ** 2)                # -log p(x|z0) w/o constants (:611-622)
     a = cfg.num_atom_types
-    sig0 = sigma(g0)
     est_cat = z_0[:, 3:3 + a] * cfg.norm_values[1] + cfg.norm_biases[1]
     onehot_u = h_cat * cfg.norm_values[1] + cfg.norm_biases[1]
     cen = est_cat - 1
@@ -579,9 +593,18 @@ def eval_nll(sd, cfg: OracleConfig, batch_index: torch.Tensor, mask: torch.Tenso
     prob = torch.tensor([float(n_nodes_hist[k]) for k in keys])
     prob = prob / prob.sum()
     log_pn = torch.log(prob + 1e-30)[torch.tensor([keys.index(int(n)) for n in num_nodes.tolist()])]
-    # assembly, evaluation branch (qm9_mol_gen_ddpm.py:247-262)
-    loss_t = T * 0.5 * snr_weight * error_t
-    nll = loss_t + (loss_0_x + loss_0_h + neg_log_constants) + kl_prior - delta_log_px - log_pn
+    if training:
+        t0 = (t_int == 0).float().squeeze(-1)
+        loss_0_x, loss_0_h, error_t = loss_0_x * t0, loss_0_h * t0, error_t * (1 - t0)       # :1095-1103
+        # assembly, training branch with loss_type "l2" (qm9_mol_gen_ddpm.py:232-245)
+        eff = (num_nodes.max() if norm_training_by_max_nodes else num_nodes).float()
+        denom = (3 + cfg.num_h) * eff
+        loss_t = 0.5 * (error_t / denom)
+        nll = loss_t + (loss_0_x / denom + loss_0_h) + kl_prior - delta_log_px - log_pn
+    else:
+        # assembly, evaluation branch (qm9_mol_gen_ddpm.py:247-262)
+        loss_t = T * 0.5 * snr_weight * error_t
+        nll = loss_t + (loss_0_x + loss_0_h + neg_log_constants) + kl_prior - delta_log_px - log_pn
     terms = dict(delta_log_px=delta_log_px, error_t=error_t, SNR_weight=snr_weight, loss_0_x=loss_0_x,
                  loss_0_h=loss_0_h, neg_log_constants=neg_log_constants, kl_prior=kl_prior, log_pN=log_pn,
                  t_int=t_int.squeeze(-1))

@@ -140,30 +140,79 @@ def nll_case(cname, sizes, seed, scale=0.5):
                            neg_log_constants=nlc, kl_prior=klp, log_pN=lpn, t_int=tint))
 
 
+def train_case(cname, sizes, seed, t_fixed, scale=0.5):
+    """Training-mode L2 objective of the reference (EquivariantVariationalDiffusion.forward with .train(): one denoiser
+    call) + the Lightning module's training assembly restated from qm9_mol_gen_ddpm.py:232-262.  torch.randint is
+    patched for the duration of the call so that the fixture contains a t == 0 molecule (the L0 branch)."""
+    hist = {19: 5, 7: 2, 12: 3, 30: 1, 6: 1, 18: 2, 44: 3, 43: 2, 25: 1}
+    ddpm, _ = ref_shim.build_reference_ddpm(cname, seed=0, n_nodes_hist=hist)
+    cfg = O.config_named(cname)
+    sd = O.random_state_dict(cfg, WEIGHT_SEED, scale=scale)
+    ddpm.dynamics_network.load_state_dict(sd, strict=True)
+    ddpm.train()
+    g = torch.Generator().manual_seed(seed)
+    nmol = len(sizes)
+    bi = torch.repeat_interleave(torch.arange(nmol), torch.tensor(sizes))
+    n = bi.shape[0]
+    mask = torch.ones(n, dtype=torch.bool)
+    mask[sizes[0] + 1] = False
+    x = torch.randn((n, 3), generator=g) * mask[:, None]
+    _, x = O.centralize(x, bi, mask, nmol)
+    types = torch.randint(0, cfg.num_atom_types, (n,), generator=g)
+    one_hot = torch.nn.functional.one_hot(types, cfg.num_atom_types).float() * mask[:, None]
+    charges = (torch.randint(1, 9, (n,), generator=g).float() * mask) if cfg.include_charges else torch.zeros((n, 0))
+    num_present = torch.zeros(nmol, dtype=torch.long).index_add_(0, bi, mask.long())
+    batch = ref_shim.Batch(batch=bi, mask=mask, x=x.clone(), h={"categorical": one_hot.clone(), "integer": charges.clone()},
+                           num_graphs=nmol, num_nodes_present=num_present, props_context=None)
+    torch.manual_seed(seed + 2000)
+    t_fixed = torch.tensor(t_fixed, dtype=torch.long).reshape(nmol, 1)
+    real_randint = torch.randint
+    torch.randint = lambda *a, **k: t_fixed.clone()
+    try:
+        with torch.no_grad():
+            (dlp, err, snr, l0x, l0h, nlc, klp, lpn, tint, _info) = ddpm(batch, return_loss_info=True)
+    finally:
+        torch.randint = real_randint
+    denom = (3 + cfg.num_h) * num_present.float()                      # norm_training_by_max_nodes: false
+    loss = 0.5 * (err / denom) + (l0x / denom + l0h) + klp - dlp - lpn
+    return dict(config=cname, sizes=list(sizes), weight_seed=WEIGHT_SEED, weight_scale=scale,
+                weight_checksum=weight_checksum(sd), histogram=hist, rng_seed=seed + 2000, batch_index=bi, mask=mask, x=x,
+                one_hot=one_hot, charges=charges, nll=loss.clone(),
+                terms=dict(delta_log_px=dlp, error_t=err, SNR_weight=snr, loss_0_x=l0x, loss_0_h=l0h,
+                           neg_log_constants=nlc, kl_prior=klp, log_pN=lpn, t_int=tint))
+
+
 def main():
+    only = sys.argv[1:]        # optional: names of the fixtures to (re)generate
+    ref_shim.install()
     fixtures = {
         # SURVEY.md §8c (i): integer KAT for the edge index, observed from the reference
-        "kat_edge_index": None,
-        "qm9_small_masked": forward_case("qm9", [5, 9, 3, 7], 11, "pad", layer_taps=True),
-        "qm9_tiny_sizes": forward_case("qm9", [1, 2, 3, 1], 12),
-        "qm9_b4_n19": forward_case("qm9", [19, 19, 19, 19], 13),
-        "qm9_cond": forward_case("qm9_cond", [19, 12, 23], 14),
-        "geom_mixed": forward_case("geom", [44, 30, 61, 25], 15),
-        "geom_max181": forward_case("geom", [181, 3], 16),
-        "chain_qm9_T6": chain_case("qm9", [19, 7, 12], 6, 123),
-        "chain_qm9_cond_T4": chain_case("qm9_cond", [9, 14], 4, 321),
-        "chain_geom_T3": chain_case("geom", [30, 44], 3, 77),
-        "nll_qm9": nll_case("qm9", [19, 7, 12], 5),
-        "nll_geom": nll_case("geom", [30, 44, 25], 6),
+        "kat_edge_index": None,       # filled below
+        "qm9_small_masked": lambda: forward_case("qm9", [5, 9, 3, 7], 11, "pad", layer_taps=True),
+        "qm9_tiny_sizes": lambda: forward_case("qm9", [1, 2, 3, 1], 12),
+        "qm9_b4_n19": lambda: forward_case("qm9", [19, 19, 19, 19], 13),
+        "qm9_cond": lambda: forward_case("qm9_cond", [19, 12, 23], 14),
+        "geom_mixed": lambda: forward_case("geom", [44, 30, 61, 25], 15),
+        "geom_max181": lambda: forward_case("geom", [181, 3], 16),
+        "chain_qm9_T6": lambda: chain_case("qm9", [19, 7, 12], 6, 123),
+        "chain_qm9_cond_T4": lambda: chain_case("qm9_cond", [9, 14], 4, 321),
+        "chain_geom_T3": lambda: chain_case("geom", [30, 44], 3, 77),
+        "nll_qm9": lambda: nll_case("qm9", [19, 7, 12], 5),
+        "nll_geom": lambda: nll_case("geom", [30, 44, 25], 6),
+        "train_qm9": lambda: train_case("qm9", [19, 7, 12], 8, [0, 517, 1000]),
+        "train_geom": lambda: train_case("geom", [30, 44, 25], 9, [311, 0, 42]),
     }
     from src.models.components.gcpnet import GCPNetDynamics
     bi = torch.tensor([0] * 5 + [1] * 5)
     mk = torch.tensor([1, 1, 1, 0, 0, 1, 1, 1, 1, 0], dtype=torch.bool)
-    fixtures["kat_edge_index"] = dict(
+    fixtures["kat_edge_index"] = lambda: dict(
         batch_index=bi, mask=mk,
         edge_index=GCPNetDynamics.get_fully_connected_edge_index(bi, mk),
         edge_index_nomask=GCPNetDynamics.get_fully_connected_edge_index(bi, None))
-    for name, fx in fixtures.items():
+    for name, make in fixtures.items():
+        if only and name not in only:
+            continue
+        fx = make()
         path = os.path.join(HERE, name + ".pt")
         torch.save(fx, path)
         print(f"{name:22s} {os.path.getsize(path) / 1024:8.1f} KiB")

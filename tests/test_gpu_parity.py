@@ -233,3 +233,21 @@ def test_eval_nll_on_device_matches_reference(name):
             continue
         assert torch.allclose(terms[k].cpu(), ref, rtol=1e-4, atol=1e-4), (k, terms[k].cpu(), ref)
     assert torch.allclose(nll.cpu(), fx["nll"], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["train_qm9", "train_geom"])
+def test_training_loss_on_device_matches_reference(name):
+    """GCDMTrainLoss (one denoiser call through the C ABI, t == 0 molecule included) vs the reference in .train() mode;
+    the fixture's t_int and CPU noise stream are replayed; tolerance 1e-4 relative on every term and on the loss."""
+    import bdiff
+    fx = load_golden(name)
+    net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], scale=fx["weight_scale"])
+    tl = bdiff.GCDMTrainLoss(net, fx["histogram"])
+    torch.manual_seed(fx["rng_seed"])
+    loss, terms = tl(fx["batch_index"].cuda(), fx["mask"].cuda(), fx["x"].cuda(), fx["one_hot"].cuda(),
+                     fx["charges"].cuda(), None, t_int=fx["terms"]["t_int"].reshape(-1, 1), noise=lambda s: torch.randn(s))
+    for k, ref in fx["terms"].items():
+        if k == "t_int":
+            continue
+        assert torch.allclose(terms[k].cpu(), ref, rtol=1e-4, atol=1e-4), (k, terms[k].cpu(), ref)
+    assert torch.allclose(loss.cpu(), fx["nll"], rtol=1e-4, atol=1e-3)

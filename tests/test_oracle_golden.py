@@ -111,3 +111,21 @@ def test_eval_nll_matches_reference(name):
             continue
         assert torch.allclose(terms[k], ref, rtol=1e-5, atol=1e-5), k
     assert torch.allclose(nll, fx["nll"], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["train_qm9", "train_geom"])
+def test_training_loss_matches_reference(name):
+    """Training-mode L2 objective (one denoiser call, t == 0 molecule included) vs the reference in .train() mode; the
+    fixture's t_int was injected into the reference, the noise comes from the same global RNG stream."""
+    fx = load_golden(name)
+    cfg, sd = weights_for(fx)
+    torch.manual_seed(fx["rng_seed"])
+    loss, terms = O.eval_nll(sd, cfg, fx["batch_index"], fx["mask"], fx["x"], fx["one_hot"], fx["charges"], None,
+                             fx["histogram"], lambda s: torch.randn(s), t_int=fx["terms"]["t_int"].reshape(-1, 1),
+                             training=True)
+    assert (fx["terms"]["t_int"] == 0).any()
+    for k, ref in fx["terms"].items():
+        if k == "t_int":
+            continue
+        assert torch.allclose(terms[k], ref, rtol=1e-5, atol=1e-5), k
+    assert torch.allclose(loss, fx["nll"], rtol=1e-5, atol=1e-4)
