@@ -112,8 +112,8 @@ def test_tensor_and_parity_modes_agree_full_size(b, variant, monkeypatch):
 def test_tensor_chain_tracks_reference_chain(name):
     """A whole sampling chain in tensor mode (CUDA-graph step, layer megakernel) against the reference's chain with the
     same recorded noise: bf16 operand rounding per forward (<= 2e-2, above) propagates through T steps, so this is a
-    divergence guard, not a parity claim: 1e-1 relative on the final latent / coordinates and at least 85 % identical
-    argmax atom types on these 23..74-atom fixtures (parity mode meets 1e-4 and 100 % on the same fixtures,
+    divergence guard, not a parity claim: 3e-2 relative on the final latent / coordinates and at least 90 % identical
+    argmax atom types (measured: 3e-3..7e-3 and 97..100 %) on these 23..74-atom fixtures (parity mode meets 1e-4 and 100 % on the same fixtures,
     tests/test_gpu_parity.py); the measured values are printed (-s)."""
     import bdiff
     fx = load_golden(name)
@@ -128,4 +128,4 @@ def test_tensor_chain_tracks_reference_chain(name):
     same = (out[:, 3:3 + a].cpu() == fx["out"][:, 3:3 + a]).all(dim=-1).float().mean().item()
     relx = (out[:, :3].cpu() - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
     print(f"{name}: tensor chain z_0 rel {rel:.3e}, x rel {relx:.3e}, identical atom types {100 * same:.1f} %")
-    assert rel < 1e-1 and relx < 1e-1 and same >= 0.85
+    assert rel < 3e-2 and relx < 3e-2 and same >= 0.9
