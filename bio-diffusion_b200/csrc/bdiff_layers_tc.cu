@@ -40,8 +40,16 @@ union LayersTail {
 constexpr size_t LAYERS_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)RING_STAGE + sizeof(LayersTail) + 1024;
 static_assert(LAYERS_SMEM_BYTES <= 232448, "shared memory budget of the layer megakernel");
 
+// 12 warps: 0-7 compute (two warpgroups), 8 scheduler + TMA producer, 9 MMA issuer, 10-11 padding so that the
+// service warps form a complete third warpgroup for setmaxnreg.  The CTA is launched with 168 registers/thread
+// (384 threads -> a pool of 64512); the service warpgroup shrinks to 96 and the two compute warpgroups grow to 200
+// (256*200 + 128*96 = 63488 <= 64512 — a request the pool cannot satisfy would block forever).
+constexpr int LAYERS_THREADS = 384;
+constexpr int LAYERS_REG_COMPUTE = 200, LAYERS_REG_SERVICE = 96;
+static_assert(256 * LAYERS_REG_COMPUTE + 128 * LAYERS_REG_SERVICE <= 168 * LAYERS_THREADS, "setmaxnreg pool");
+
 template <int ED, int XD>
-__global__ void __launch_bounds__(TC_THREADS2, 1) k_layers_tc(Plan p, Dims d, EmbedW ew, LayerSched q, Work w) {
+__global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d, EmbedW ew, LayerSched q, Work w) {
   constexpr int HID0 = (64 + XD) / 4;
   constexpr int H2 = HID0 / 2;
   constexpr int K0RAW = ED + HID0 + 9;
@@ -82,6 +90,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) k_layers_tc(Plan p, Dims d, Em
 
   if (warp == 8) {
     // ============================================================ scheduler + TMA producer (one lane)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
     if (lane == 0) {
       TcBars& T = B;
       uint32_t ci = 0;
@@ -109,6 +118,7 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) k_layers_tc(Plan p, Dims d, Em
     }
   } else if (warp == 9) {
     // ======================================================================= MMA issuer (one lane)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
     if (lane == 0) {
       TcBars& T = B;
       const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
@@ -170,8 +180,11 @@ __global__ void __launch_bounds__(TC_THREADS2, 1) k_layers_tc(Plan p, Dims d, Em
         mbar_arrive(&B.item_empty[slot]);
       }
     }
+  } else if (warp >= 10) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));     // padding warps of the service warpgroup
   } else {
     // ============================================================================ compute / epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_COMPUTE));
     uint32_t pd = 0, pw = 0;
     int es = 64;                 // the per-tile bodies' own stamps are off here; this kernel stamps per item (below)
     int cur_type = -1, cur_layer = -1;
@@ -294,8 +307,8 @@ void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const Embed
                       const Work& w, int num_sms) {
   const int items = q.L * (q.TE + q.TN);
   const int grid = items < num_sms ? items : num_sms;
-  if (d.Ed == 64) k_layers_tc<64, 16><<<grid, TC_THREADS2, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
-  else k_layers_tc<16, 8><<<grid, TC_THREADS2, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
+  if (d.Ed == 64) k_layers_tc<64, 16><<<grid, LAYERS_THREADS, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
+  else k_layers_tc<16, 8><<<grid, LAYERS_THREADS, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
 }
 
 }  // namespace bdiff
