@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Per-item timing of the layer megakernel k_layers_tc (BDIFF_TIMING=1): for a few CTAs, the first 16 work items
+with their fetch time, dependency/fence wait and run time in SM cycles.  GPU only."""
 import os, sys
 os.environ["BDIFF_TIMING"] = "1"
 ROOT = "/root/repo"

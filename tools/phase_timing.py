@@ -6,6 +6,7 @@ import os
 import sys
 
 os.environ["BDIFF_TIMING"] = "1"
+os.environ.setdefault("BDIFF_MEGA", "0")      # per-pass kernels: their per-phase stamps (tools/mega_timing.py: per-item)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "bio-diffusion_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
