@@ -184,6 +184,19 @@ BDIFF_API int32_t bdiff_optimizer_step(void* stream, const bdiff_opt_tensor* ten
                                        const int64_t* chunk_start_dev, int32_t num_chunks, double* partial_dev,
                                        int32_t* state_dev, const bdiff_opt_hyper* hyper);
 
+/* ---- post-sampling stability check ----------------------------------------------------------------
+ * Batched `check_molecular_stability` (src/datamodules/components/edm/__init__.py:91-124 with get_bond_order_batch
+ * :61-88): for every molecule k (atoms mol_off[k] .. mol_off[k+1]) the bond order of each atom pair from the three
+ * bond-length tables [num_types x num_types] (pm; 0 = no such bond) and margins, the per-atom bond count, and whether
+ * that count is allowed for the atom's type (bit c of allowed_mask[type] set <=> c bonds allowed).  Outputs:
+ * nr_bonds[N], nr_stable[B] (atoms with an allowed count), mol_stable[B] (1 iff all atoms).  The tables are data of
+ * the caller's dataset (the reference keeps them in dataset_info / edm/constants.py); all pointers are device pointers. */
+BDIFF_API int32_t bdiff_check_stability(void* stream, const float* x, const int32_t* atom_types, const int32_t* mol_off,
+                                        int32_t num_mols, int32_t num_types, const float* bonds1, const float* bonds2,
+                                        const float* bonds3, float margin1, float margin2, float margin3,
+                                        const uint32_t* allowed_mask, int32_t limit_bonds_to_one, int32_t* nr_bonds,
+                                        int32_t* nr_stable, int32_t* mol_stable);
+
 /* Counters for bench.py: kernels launched by this handle since creation. */
 BDIFF_API int64_t bdiff_launch_count(const bdiff_handle* h);
 
