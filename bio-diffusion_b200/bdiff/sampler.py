@@ -63,10 +63,12 @@ class GCDMSampler:
     @torch.inference_mode()
     def sample(self, num_nodes: torch.Tensor, context: Optional[torch.Tensor] = None,
                num_timesteps: Optional[int] = None, node_mask: Optional[torch.Tensor] = None,
-               noise: Optional[NoiseFn] = None, return_z0: bool = False):
+               noise: Optional[NoiseFn] = None, return_z0: bool = False, z_init: Optional[torch.Tensor] = None):
         """mol_gen_sample (variational_diffusion.py:1280-1412) with return_frames=1.
 
         num_nodes int64[B]; context [B,C] or None; `noise(shape)` optionally injects the randn draws (tests).
+        `z_init` [N, 3+F] (normalised, CoG-free) starts the chain from given states instead of z_T ~ N(0, I) — no
+        initial noise draw (this is what `optimize` / the reference's mol_gen_optimize does).
         Returns (out [N, 3+A(+1)], batch_index [N], node_mask [N]) like the reference (+ z_0 when asked).
         """
         cfg = self.cfg
@@ -107,11 +109,16 @@ class GCDMSampler:
                 buf_x.copy_(noise((n, 3)))
                 buf_h.copy_(noise((n, f)))
 
-        # z_T ~ N(0, I) on the zero-CoG subspace (variational_diffusion.py:1322-1328)
-        draw(st["nx"], st["nh"])
-        _lib.check(h, lib.bdiff_center_noise(h, self.net._stream(), C.c_void_p(st["nx"].data_ptr()),
-                                             C.c_void_p(st["nh"].data_ptr()), C.c_void_p(st["z"].data_ptr())),
-                   "bdiff_center_noise")
+        if z_init is None:
+            # z_T ~ N(0, I) on the zero-CoG subspace (variational_diffusion.py:1322-1328)
+            draw(st["nx"], st["nh"])
+            _lib.check(h, lib.bdiff_center_noise(h, self.net._stream(), C.c_void_p(st["nx"].data_ptr()),
+                                                 C.c_void_p(st["nh"].data_ptr()), C.c_void_p(st["z"].data_ptr())),
+                       "bdiff_center_noise")
+        else:
+            if tuple(z_init.shape) != (n, 3 + f):
+                raise ValueError(f"z_init must be [{n}, {3 + f}]")
+            st["z"].copy_(z_init.to(dev, torch.float32))
         st["step"].zero_()
 
         graph_ok = self.use_cuda_graph and noise is None
@@ -193,6 +200,33 @@ class GCDMSampler:
         return zz
 
     @torch.inference_mode()
+    @torch.inference_mode()
+    def optimize(self, samples, num_nodes: torch.Tensor, context: Optional[torch.Tensor] = None,
+                 num_timesteps: Optional[int] = None, node_mask: Optional[torch.Tensor] = None,
+                 noise: Optional[NoiseFn] = None):
+        """mol_gen_optimize (variational_diffusion.py:1414-1546, return_frames=1, norm_with_original_timesteps=False):
+        run `num_timesteps` reverse steps starting from existing molecules.  `samples` = list of (x [n_k,3] CoG-free,
+        one_hot [n_k,A]) per molecule as in the reference.  Only configurations without integer features
+        (include_charges=False) — the reference stacks positions and categorical features only."""
+        cfg = self.cfg
+        if cfg.include_charges:
+            raise NotImplementedError("mol_gen_optimize stacks [x | one-hot] only: needs include_charges=False")
+        dev = self._device()
+        x = torch.vstack([s[0] for s in samples]).to(dev, torch.float32)
+        hc = torch.vstack([s[1] for s in samples]).to(dev, torch.float32)
+        n = x.shape[0]
+        mask = torch.ones(n, dtype=torch.bool, device=dev) if node_mask is None else node_mask.to(dev)
+        mf = mask.float().unsqueeze(-1)
+        bi = torch.repeat_interleave(torch.arange(len(samples), device=dev), num_nodes.to(dev))
+        if bi.shape[0] != n:
+            raise ValueError("num_nodes does not match the samples")
+        z = torch.cat((x / cfg.norm_values[0] * mf, (hc - cfg.norm_biases[1]) / cfg.norm_values[1] * mf), dim=-1)   # normalize (:702-732)
+        largest = z[:, :3].abs().max().item()                                 # assert_mean_zero_with_mask (:465-474):
+        err = z[:, :3].sum(dim=0).abs().max().item()                          # the reference sums over the WHOLE batch
+        if err / (largest + 1e-10) >= 1e-2:
+            raise AssertionError(f"Mean is not zero, as relative_error {err / (largest + 1e-10)}")
+        return self.sample(num_nodes, context, num_timesteps, node_mask, noise, z_init=z)
+
     def sample_from_host(self, num_nodes_host: torch.Tensor, context_host: Optional[torch.Tensor] = None,
                          num_timesteps: Optional[int] = None, out_host: Optional[torch.Tensor] = None):
         """End-to-end entry used by bench.py: pinned host inputs -> device -> chain -> pinned host result."""

@@ -383,9 +383,12 @@ def decode_z0(sd, cfg: OracleConfig, gamma, z0, batch_index, mask, context, rand
 
 def sample_chain(sd, cfg: OracleConfig, num_nodes: torch.Tensor, randn: NoiseFn,
                  num_timesteps: Optional[int] = None, context: Optional[torch.Tensor] = None,
-                 mask: Optional[torch.Tensor] = None, return_z0: bool = False):
+                 mask: Optional[torch.Tensor] = None, return_z0: bool = False, z_init: Optional[torch.Tensor] = None):
     """mol_gen_sample (variational_diffusion.py:1280-1412), return_frames=1, no self-conditioning.
 
+    With `z_init` (normalised [x | one-hot], see `normalize_samples`) this is mol_gen_optimize (:1414-1546,
+    norm_with_original_timesteps=False): the same loop started from existing samples instead of z_T ~ N(0, I) — no
+    initial noise draw, everything else (time grid s/num_timesteps, per-step noise order, final decode, CoG fix) equal.
     Returns (out [N, 3+A(+1)], batch_index, mask)  (and z_0 when asked).
     """
     T = cfg.num_timesteps if num_timesteps is None else num_timesteps
@@ -396,7 +399,7 @@ def sample_chain(sd, cfg: OracleConfig, num_nodes: torch.Tensor, randn: NoiseFn,
     if context is not None:                                      # (:1316-1320)
         ctx = context[batch_index] * mask.float()[:, None]
     gamma = gamma_table(cfg.num_timesteps, cfg.noise_precision, cfg.schedule_power)
-    z = combined_noise(randn, cfg, batch_index, mask, nmol)      # p(z_T)
+    z = combined_noise(randn, cfg, batch_index, mask, nmol) if z_init is None else z_init.clone()      # p(z_T) / samples
     for s in reversed(range(T)):                                 # (:1335-1351)
         z = reverse_step(sd, cfg, gamma, s, s + 1, z, batch_index, mask, ctx, randn, T, nmol)
     x, h_cat, h_int = decode_z0(sd, cfg, gamma, z, batch_index, mask, ctx, randn, nmol)
@@ -406,6 +409,12 @@ def sample_chain(sd, cfg: OracleConfig, num_nodes: torch.Tensor, randn: NoiseFn,
     parts = [x, h_cat.float()] + ([h_int.float()] if cfg.include_charges else [])
     out = torch.cat(parts, dim=-1)
     return (out, batch_index, mask, z) if return_z0 else (out, batch_index, mask)
+
+
+def normalize_samples(cfg: OracleConfig, x: torch.Tensor, one_hot: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """The input side of mol_gen_optimize (:1456-1464): normalize (:702-732) x and the categorical features, stack."""
+    mf = mask.float()[:, None]
+    return torch.cat((x / cfg.norm_values[0] * mf, (one_hot.float() - cfg.norm_biases[1]) / cfg.norm_values[1] * mf), dim=-1)
 
 
 # ----------------------------------------------------------------------------------------------

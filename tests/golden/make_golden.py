@@ -105,6 +105,35 @@ def chain_case(cname, sizes, steps, seed, scale=0.5):
                 z_0=zs[-1], gamma=ddpm.gamma.gamma.data.clone())
 
 
+def optimize_case(cname, sizes, steps, seed, scale=0.5):
+    """mol_gen_optimize (variational_diffusion.py:1414-1546) of the reference on given samples (unmodified)."""
+    ddpm, _ = ref_shim.build_reference_ddpm(cname, seed=0)
+    cfg = O.config_named(cname)
+    assert not cfg.include_charges
+    sd = O.random_state_dict(cfg, WEIGHT_SEED, scale=scale)
+    ddpm.dynamics_network.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed)
+    nmol = len(sizes)
+    num_nodes = torch.tensor(sizes)
+    bi = torch.repeat_interleave(torch.arange(nmol), num_nodes)
+    n = bi.shape[0]
+    mask = torch.ones(n, dtype=torch.bool)
+    x = torch.randn((n, 3), generator=g) * 1.5
+    _, x = O.centralize(x, bi, mask, nmol)
+    one_hot = torch.nn.functional.one_hot(torch.randint(0, cfg.num_atom_types, (n,), generator=g), cfg.num_atom_types).float()
+    ctx = torch.randn((nmol, cfg.num_context), generator=g) if cfg.num_context else None
+    samples, o = [], 0
+    for k in sizes:
+        samples.append((x[o:o + k].clone(), one_hot[o:o + k].clone()))
+        o += k
+    torch.manual_seed(seed)
+    out, bi2, mask2 = ddpm.mol_gen_optimize(samples=samples, num_nodes=num_nodes, device="cpu", num_timesteps=steps,
+                                            context=ctx)
+    assert torch.equal(bi2, bi)
+    return dict(config=cname, sizes=list(sizes), steps=steps, noise_seed=seed, weight_seed=WEIGHT_SEED, weight_scale=scale,
+                weight_checksum=weight_checksum(sd), context=ctx, x=x, one_hot=one_hot, out=out.clone())
+
+
 def nll_case(cname, sizes, seed, scale=0.5):
     """Evaluation-mode NLL terms of the reference (EquivariantVariationalDiffusion.forward with .eval(), two denoiser
     calls) + the Lightning module's evaluation assembly restated from qm9_mol_gen_ddpm.py:247-262."""
@@ -201,6 +230,8 @@ def main():
         "nll_geom": lambda: nll_case("geom", [30, 44, 25], 6),
         "train_qm9": lambda: train_case("qm9", [19, 7, 12], 8, [0, 517, 1000]),
         "train_geom": lambda: train_case("geom", [30, 44, 25], 9, [311, 0, 42]),
+        "optimize_qm9_cond_T4": lambda: optimize_case("qm9_cond", [9, 14, 19], 4, 41),
+        "optimize_geom_T3": lambda: optimize_case("geom", [30, 21], 3, 42),
     }
     from src.models.components.gcpnet import GCPNetDynamics
     bi = torch.tensor([0] * 5 + [1] * 5)

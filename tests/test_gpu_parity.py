@@ -251,3 +251,25 @@ def test_training_loss_on_device_matches_reference(name):
             continue
         assert torch.allclose(terms[k].cpu(), ref, rtol=1e-4, atol=1e-4), (k, terms[k].cpu(), ref)
     assert torch.allclose(loss.cpu(), fx["nll"], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", ["optimize_qm9_cond_T4", "optimize_geom_T3"])
+def test_optimize_chain_matches_reference_golden(name):
+    """GCDMSampler.optimize (= mol_gen_optimize: the chain started from given molecules) vs the reference, CPU noise
+    stream replayed; identical atom types, coordinates <= 1e-4 relative."""
+    import bdiff
+    fx = load_golden(name)
+    net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], scale=fx["weight_scale"])
+    sampler = bdiff.GCDMSampler(net)
+    samples, o = [], 0
+    for k in fx["sizes"]:
+        samples.append((fx["x"][o:o + k], fx["one_hot"][o:o + k]))
+        o += k
+    ctx = fx["context"].cuda() if fx["context"] is not None else None
+    torch.manual_seed(fx["noise_seed"])
+    out, bi, mask = sampler.optimize(samples, torch.tensor(fx["sizes"]), ctx, num_timesteps=fx["steps"],
+                                     noise=lambda s: torch.randn(s).cuda())
+    a = ocfg.num_atom_types
+    assert torch.equal(out[:, 3:3 + a].cpu(), fx["out"][:, 3:3 + a])
+    relx = (out[:, :3].cpu() - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
+    assert relx < 1e-4, relx

@@ -129,3 +129,22 @@ def test_training_loss_matches_reference(name):
             continue
         assert torch.allclose(terms[k], ref, rtol=1e-5, atol=1e-5), k
     assert torch.allclose(loss, fx["nll"], rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["optimize_qm9_cond_T4", "optimize_geom_T3"])
+def test_optimize_chain_matches_reference(name):
+    """mol_gen_optimize of the reference (chain started from given samples) vs the oracle, same global RNG stream."""
+    fx = load_golden(name)
+    cfg, sd = weights_for(fx)
+    nmol = len(fx["sizes"])
+    num_nodes = torch.tensor(fx["sizes"])
+    bi = torch.repeat_interleave(torch.arange(nmol), num_nodes)
+    mask = torch.ones(bi.shape[0], dtype=torch.bool)
+    z = O.normalize_samples(cfg, fx["x"], fx["one_hot"], mask)
+    torch.manual_seed(fx["noise_seed"])
+    out, _, _ = O.sample_chain(sd, cfg, num_nodes, lambda s: torch.randn(s), num_timesteps=fx["steps"], context=fx["context"],
+                               z_init=z)
+    a = cfg.num_atom_types
+    assert torch.equal(out[:, 3:3 + a], fx["out"][:, 3:3 + a])
+    rel = (out[:, :3] - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
+    assert rel < 1e-5, rel
