@@ -134,6 +134,14 @@ def optimize_case(cname, sizes, steps, seed, scale=0.5):
                 weight_checksum=weight_checksum(sd), context=ctx, x=x, one_hot=one_hot, out=out.clone())
 
 
+def grad_case(cname, sizes, seed, t_fixed, scale=0.5):
+    """Config 5's parity target: mean training loss of the reference in .train() mode and its gradient with respect to
+    every denoiser parameter (loss.backward() through the unmodified reference).  The gradients are stored as
+    per-tensor fingerprints (L2 norm, sum, and the 8 entries at fixed strided positions) to keep the fixture small."""
+    fx = train_case(cname, sizes, seed, t_fixed, scale, _with_grad=True)
+    return fx
+
+
 def nll_case(cname, sizes, seed, scale=0.5):
     """Evaluation-mode NLL terms of the reference (EquivariantVariationalDiffusion.forward with .eval(), two denoiser
     calls) + the Lightning module's evaluation assembly restated from qm9_mol_gen_ddpm.py:247-262."""
@@ -169,7 +177,13 @@ def nll_case(cname, sizes, seed, scale=0.5):
                            neg_log_constants=nlc, kl_prior=klp, log_pN=lpn, t_int=tint))
 
 
-def train_case(cname, sizes, seed, t_fixed, scale=0.5):
+def grad_fingerprint(g):
+    f = g.detach().double().reshape(-1)
+    idx = torch.linspace(0, f.numel() - 1, steps=min(8, f.numel())).long()
+    return dict(norm=float(f.norm()), sum=float(f.sum()), idx=idx, vals=f[idx].float().clone())
+
+
+def train_case(cname, sizes, seed, t_fixed, scale=0.5, _with_grad=False):
     """Training-mode L2 objective of the reference (EquivariantVariationalDiffusion.forward with .train(): one denoiser
     call) + the Lightning module's training assembly restated from qm9_mol_gen_ddpm.py:232-262.  torch.randint is
     patched for the duration of the call so that the fixture contains a t == 0 molecule (the L0 branch)."""
@@ -198,15 +212,21 @@ def train_case(cname, sizes, seed, t_fixed, scale=0.5):
     real_randint = torch.randint
     torch.randint = lambda *a, **k: t_fixed.clone()
     try:
-        with torch.no_grad():
+        with torch.set_grad_enabled(_with_grad):
             (dlp, err, snr, l0x, l0h, nlc, klp, lpn, tint, _info) = ddpm(batch, return_loss_info=True)
     finally:
         torch.randint = real_randint
     denom = (3 + cfg.num_h) * num_present.float()                      # norm_training_by_max_nodes: false
     loss = 0.5 * (err / denom) + (l0x / denom + l0h) + klp - dlp - lpn
+    grads = None
+    if _with_grad:
+        loss.mean().backward()                                         # training_step: loss = nll.mean(0)
+        grads = {k: grad_fingerprint(p.grad) for k, p in ddpm.dynamics_network.named_parameters()}
+        assert all(p.grad is not None for p in ddpm.dynamics_network.parameters())
+        loss, dlp, err, snr, l0x, l0h, nlc, klp, lpn = (v.detach() for v in (loss, dlp, err, snr, l0x, l0h, nlc, klp, lpn))
     return dict(config=cname, sizes=list(sizes), weight_seed=WEIGHT_SEED, weight_scale=scale,
                 weight_checksum=weight_checksum(sd), histogram=hist, rng_seed=seed + 2000, batch_index=bi, mask=mask, x=x,
-                one_hot=one_hot, charges=charges, nll=loss.clone(),
+                one_hot=one_hot, charges=charges, nll=loss.clone(), grads=grads,
                 terms=dict(delta_log_px=dlp, error_t=err, SNR_weight=snr, loss_0_x=l0x, loss_0_h=l0h,
                            neg_log_constants=nlc, kl_prior=klp, log_pN=lpn, t_int=tint))
 
@@ -230,6 +250,8 @@ def main():
         "nll_geom": lambda: nll_case("geom", [30, 44, 25], 6),
         "train_qm9": lambda: train_case("qm9", [19, 7, 12], 8, [0, 517, 1000]),
         "train_geom": lambda: train_case("geom", [30, 44, 25], 9, [311, 0, 42]),
+        "grad_geom": lambda: grad_case("geom", [12, 8, 6], 10, [311, 0, 42]),
+        "grad_qm9": lambda: grad_case("qm9", [7, 7], 11, [100, 900]),
         "optimize_qm9_cond_T4": lambda: optimize_case("qm9_cond", [9, 14, 19], 4, 41),
         "optimize_geom_T3": lambda: optimize_case("geom", [30, 21], 3, 42),
     }

@@ -148,3 +148,29 @@ def test_optimize_chain_matches_reference(name):
     assert torch.equal(out[:, 3:3 + a], fx["out"][:, 3:3 + a])
     rel = (out[:, :3] - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
     assert rel < 1e-5, rel
+
+
+@pytest.mark.parametrize("name", ["grad_geom", "grad_qm9"])
+def test_training_gradients_match_reference(name):
+    """Config 5's parity target for the (not yet built) CUDA backward: autograd through the ORACLE's training objective
+    gives the same gradient for every denoiser parameter as loss.backward() through the unmodified reference
+    (fingerprints: L2 norm, sum and 8 strided entries per tensor; 202 / 432 tensors, none without gradient)."""
+    fx = load_golden(name)
+    cfg, sd = weights_for(fx)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    torch.manual_seed(fx["rng_seed"])
+    loss, terms = O.eval_nll(sd, cfg, fx["batch_index"], fx["mask"], fx["x"], fx["one_hot"], fx["charges"], None,
+                             fx["histogram"], lambda s: torch.randn(s), t_int=fx["terms"]["t_int"].reshape(-1, 1),
+                             training=True)
+    assert torch.allclose(loss.detach(), fx["nll"], rtol=1e-5, atol=1e-4)
+    loss.mean().backward()
+    assert set(fx["grads"].keys()) == set(sd.keys())
+    worst = 0.0
+    for k, ref in fx["grads"].items():
+        g = sd[k].grad
+        assert g is not None, k
+        f = g.detach().double().reshape(-1)
+        scale = max(ref["norm"], 1e-12)
+        worst = max(worst, abs(float(f.norm()) - ref["norm"]) / scale, abs(float(f.sum()) - ref["sum"]) / scale,
+                    float((f[ref["idx"]].float() - ref["vals"]).abs().max()) / scale)
+    assert worst < 2e-4, worst
