@@ -5,6 +5,11 @@ for the `_orientations` boundary quirk, so each rank runs the
 sub-batch with no communication and the final [N_r, 3+A(+1)] blocks are exchanged once (NCCL all_gather of
 padded blocks over NVLink; gloo on CPU for tests).  Parity policy: PER-SHARD — the oracle for rank r is the
 reference run on rank r's sub-batch (what a user sharding the reference by hand would get).
+
+Training (config 5) is plain replica data parallelism in the reference (Lightning DDP, one all-reduce of all gradients
+per step, configs/trainer/ddp.yaml); `allreduce_mean_` below is that exchange for a list of gradient tensors: packed
+into buckets, ONE collective per bucket, averaged, unpacked in place.  (The CUDA backward that would feed it is not
+built yet; the helper is exercised on CPU/gloo and works unchanged over NCCL.)
 """
 from __future__ import annotations
 
@@ -70,3 +75,36 @@ def sample_sharded(sampler, num_nodes: torch.Tensor, context: Optional[torch.Ten
     if not gather:
         return out, mine
     return gather_results(out, mine, sizes, world, group), mine
+
+
+def allreduce_mean_(tensors: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20) -> int:
+    """In-place mean over the ranks of `group` of every tensor in `tensors` (the gradients of one step), packed into
+    contiguous buckets of at most `bucket_bytes` so that a 2.7 M-parameter model is ONE all-reduce.  All tensors must
+    share dtype and device.  Returns the number of collectives issued (0 when the world size is 1)."""
+    tensors = [t for t in tensors if t is not None and t.numel() > 0]
+    if not tensors:
+        return 0
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    world = dist.get_world_size(group)
+    dtype, dev = tensors[0].dtype, tensors[0].device
+    if any(t.dtype != dtype or t.device != dev for t in tensors):
+        raise ValueError("allreduce_mean_: tensors must share dtype and device")
+    per = max(1, bucket_bytes // tensors[0].element_size())
+    buckets: List[List[torch.Tensor]] = [[]]
+    fill = 0
+    for t in tensors:
+        if buckets[-1] and fill + t.numel() > per:
+            buckets.append([])
+            fill = 0
+        buckets[-1].append(t)
+        fill += t.numel()
+    for b in buckets:
+        flat = torch.cat([t.reshape(-1) for t in b])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        o = 0
+        for t in b:
+            t.copy_(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+    return len(buckets)

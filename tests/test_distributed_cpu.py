@@ -56,3 +56,41 @@ def test_two_rank_gather_restores_global_order():
         out, mine = results[rank]
         assert torch.equal(out, expect)
     assert sorted(results[0][1] + results[1][1]) == list(range(len(sizes)))
+
+
+def _grad_worker(rank, world, port, results):
+    sys.path.insert(0, os.path.join(ROOT, "bio-diffusion_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bdiff.distributed import allreduce_mean_
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = [(256, 605), (256,), (32, 8), (1, 256), (17,)]
+    grads = [torch.randn(s, generator=g) for s in shapes]
+    mine = [t.clone() for t in grads]
+    n_one = allreduce_mean_(grads)                       # everything in one bucket
+    again = [t.clone() for t in mine]
+    n_many = allreduce_mean_(again, bucket_bytes=4096)   # forced into several buckets: same result
+    results[rank] = (mine, grads, again, n_one, n_many)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_mean():
+    """Config 5's only collective: the mean of every rank's gradients, one all-reduce for the whole model."""
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, 29533, results), nprocs=2, join=True)
+    (a0, r0, m0, n_one0, n_many0), (a1, r1, m1, n_one1, n_many1) = results[0], results[1]
+    assert n_one0 == n_one1 == 1 and n_many0 == n_many1 and n_many0 > 1
+    for x0, x1, y0, y1, z0 in zip(a0, a1, r0, r1, m0):
+        want = (x0 + x1) / 2
+        assert torch.allclose(y0, want, rtol=0, atol=1e-7) and torch.equal(y0, y1)
+        assert torch.allclose(z0, want, rtol=0, atol=1e-7)
+
+
+def test_allreduce_mean_single_process_is_noop():
+    sys.path.insert(0, os.path.join(ROOT, "bio-diffusion_b200"))
+    from bdiff.distributed import allreduce_mean_
+    t = [torch.ones(3)]
+    assert allreduce_mean_(t) == 0 and torch.equal(t[0], torch.ones(3))
