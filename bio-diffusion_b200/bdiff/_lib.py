@@ -34,7 +34,7 @@ PROTOTYPES = {
     "bdiff_set_weight": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "bdiff_weights_missing": (C.c_int32, [C.c_void_p]),
     "bdiff_prepare": (C.c_int32, [C.c_void_p, C.c_void_p]),
-    "bdiff_selftest_umma": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bdiff_selftest_split": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bdiff_plan_topology": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_int64)]),
     "bdiff_edge_index": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -54,6 +54,7 @@ PROTOTYPES = {
     "bdiff_optimizer_chunk": (C.c_int32, []),
     "bdiff_optimizer_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
+    "bdiff_nan_guard_count": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "bdiff_launch_count": (C.c_int64, [C.c_void_p]),
 }
 

@@ -61,6 +61,7 @@ class GCPNetDynamicsB200(nn.Module):
         self._weights_key = None
         self._plan_key = None
         self._plan_info = None       # (B, N, E)
+        self._plan_epoch = 0         # bumped by every bdiff_plan_topology call (device buffers may have moved)
         self._keepalive = None
 
     # ------------------------------------------------------------------------------------------ parameters
@@ -143,6 +144,7 @@ class GCPNetDynamicsB200(nn.Module):
         _lib.check(h, lib.bdiff_plan_topology(h, self._stream(), b, n, C.c_void_p(bi.data_ptr()),
                                               C.c_void_p(mk.data_ptr()), C.byref(e)), "bdiff_plan_topology")
         self._plan_key = key
+        self._plan_epoch += 1
         self._plan_info = (b, n, int(e.value))
         self._keepalive = (batch_index, mask)
         return self._plan_info
@@ -199,7 +201,7 @@ class GCPNetDynamicsB200(nn.Module):
         """Reference contract: gcpnet.py:1042-1052.  Reads batch.batch / batch.mask / batch.props_context."""
         if kwargs.get("xh_self_cond") is not None or kwargs.get("x_self_cond") is not None:
             raise NotImplementedError("self-conditioning is not supported (shipped configs have self_condition=false)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and xh.requires_grad:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("backward through GCPNetDynamicsB200 is not implemented yet (inference path)")
         ctx = getattr(batch, "props_context", None)
         num_mols = getattr(batch, "num_graphs", None)
@@ -233,10 +235,8 @@ class GCPNetDynamicsB200(nn.Module):
     @property
     def kernels_per_forward(self) -> int:
         """libbdiff kernels in one denoiser forward: prep, node_frames, edge_embed, node_embed, finalize plus either
-        one persistent k_layers_tc (tensor mode) or 2 per layer (parity mode, or BDIFF_MEGA=0)."""
-        import os
-        fused = self.mode == "tensor" and os.environ.get("BDIFF_MEGA", "1")[:1] != "0"
-        return 5 + (1 if fused else 2 * self.cfg.num_layers)
+        one persistent k_layers_tc (tensor mode) or 2 per layer (parity mode)."""
+        return 5 + (1 if self.mode == "tensor" else 2 * self.cfg.num_layers)
 
     def launch_count(self) -> int:
         return int(_lib.load().bdiff_launch_count(self._handle)) if self._handle is not None else 0

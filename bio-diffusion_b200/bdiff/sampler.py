@@ -31,6 +31,7 @@ class GCDMSampler:
         self._graph = None
         self._static = None
         self.kernel_launches = 0     # libbdiff kernels launched (or replayed from the graph) by sample()
+        self.last_moments = None     # [T, 4] per-step (mean_x, std_x, mean_h, std_h) of z when sample(record_moments=True)
 
     # -------------------------------------------------------------------------------------------- helpers
     def _device(self) -> torch.device:
@@ -63,7 +64,8 @@ class GCDMSampler:
     @torch.inference_mode()
     def sample(self, num_nodes: torch.Tensor, context: Optional[torch.Tensor] = None,
                num_timesteps: Optional[int] = None, node_mask: Optional[torch.Tensor] = None,
-               noise: Optional[NoiseFn] = None, return_z0: bool = False, z_init: Optional[torch.Tensor] = None):
+               noise: Optional[NoiseFn] = None, return_z0: bool = False, z_init: Optional[torch.Tensor] = None,
+               record_moments: bool = False):
         """mol_gen_sample (variational_diffusion.py:1280-1412) with return_frames=1.
 
         num_nodes int64[B]; context [B,C] or None; `noise(shape)` optionally injects the randn draws (tests).
@@ -121,15 +123,28 @@ class GCDMSampler:
             st["z"].copy_(z_init.to(dev, torch.float32))
         st["step"].zero_()
 
+        moments = torch.zeros((steps, 4), device=dev) if record_moments else None
+
+        def record():
+            # diagnostics only (tests): moments of the latent after this step, written at row `step` on the device
+            zx, zh = st["z"][:, :3], st["z"][:, 3:]
+            m = torch.stack((zx.mean(), zx.std(), zh.mean(), zh.std())).view(1, 4)
+            moments.index_copy_(0, st["step"].long().view(1), m)
+
         graph_ok = self.use_cuda_graph and noise is None
         if graph_ok:
-            gkey = (st["key"], self.net._plan_key, self.net._weights_key, ctx.data_ptr() if ctx is not None else 0)
+            # the captured graph bakes in raw pointers of the library's plan / workspace buffers, which move when a larger
+            # topology was planned in between: the plan epoch (bumped by every bdiff_plan_topology) is part of the key
+            gkey = (st["key"], self.net._plan_key, self.net._plan_epoch, self.net._weights_key,
+                    ctx.data_ptr() if ctx is not None else 0, moments.data_ptr() if record_moments else 0)
             if self._graph is None or self._graph_key != gkey:
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     draw(st["nx"], st["nh"])
                     self._reverse_step(st, ctx_ptr)
+                    if record_moments:
+                        record()
                     st["step"].add_(1)
                 self._graph, self._graph_key = g, gkey
                 self._ctx_keep = ctx
@@ -139,7 +154,10 @@ class GCDMSampler:
             for _ in range(steps):
                 draw(st["nx"], st["nh"])
                 self._reverse_step(st, ctx_ptr)
+                if record_moments:
+                    record()
                 st["step"].add_(1)
+        self.last_moments = moments
 
         # one forward = prep, node_frames, edge_embed, node_embed, L x (edge_message, node_update), finalize
         per_forward = self.net.kernels_per_forward
@@ -171,6 +189,14 @@ class GCDMSampler:
         parts[0] = x
         out = torch.cat(parts, dim=-1)
         return (out, batch_index, mask, z0) if return_z0 else (out, batch_index, mask)
+
+    def nan_guard_count(self, reset: bool = False) -> int:
+        """Denoiser forwards in which the NaN guard of gcpnet.py:1214-1216 fired since the workspace was (re)planned."""
+        lib = _lib.load()
+        v = C.c_int64(0)
+        _lib.check(self.net._handle, lib.bdiff_nan_guard_count(self.net._handle, self.net._stream(), C.byref(v),
+                                                              1 if reset else 0), "bdiff_nan_guard_count")
+        return int(v.value)
 
     @torch.inference_mode()
     def reverse_step_once(self, z: torch.Tensor, row: int, steps: int, batch_index: torch.Tensor,

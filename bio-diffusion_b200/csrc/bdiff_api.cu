@@ -61,7 +61,6 @@ struct bdiff_handle {
   Plan plan{};
   DevBuf plan_buf, rc_buf, layers_dev, sched_buf, items_buf;
   LayerSched sched{};
-  bool mega = true;             // tensor mode: all layers in one persistent kernel (BDIFF_MEGA=0 -> one kernel per pass)
   int Npad = 0;
   long long Epad = 0;
 
@@ -247,6 +246,7 @@ cudaError_t ensure_work(bdiff_handle* h) {
                o_fbar = take(Np * 12), o_h = take(Np * 256), o_chi = take(Np * 96), o_PI = take(Np * kPStride),
                o_PJ = take(Np * kPStride), o_agg = take(Np * kMsg), o_hp = take(Np * 32),
                o_e = take(Ep * d.Ed), o_xie = take(Ep * d.Xd * 3), o_fr = take(Ep * 9), o_pjt = take(Np * 256),
+               o_mid = take(h->cfg.mode == BDIFF_MODE_TENSOR ? (Ep / 128) * kMsg : 0),
                o_flag = take(64);
   cudaError_t e = h->work_buf.ensure(off * sizeof(float));
   if (e != cudaSuccess) return e;
@@ -256,6 +256,7 @@ cudaError_t ensure_work(bdiff_handle* h) {
   w.h = b + o_h; w.chi = b + o_chi; w.PI = b + o_PI; w.PJ = b + o_PJ; w.agg = b + o_agg; w.hproj = b + o_hp;
   w.e = b + o_e; w.xi = b + o_xie; w.frames = b + o_fr;
   w.PJT = h->cfg.mode == BDIFF_MODE_TENSOR ? b + o_pjt : nullptr;
+  w.mid = h->cfg.mode == BDIFF_MODE_TENSOR ? b + o_mid : nullptr;
   w.npad = (int)Np;
   w.nan_flag = reinterpret_cast<int*>(b + o_flag);
   w.dbg = nullptr;
@@ -341,10 +342,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
       delete h;
       return BDIFF_EINVAL;
     }
-    e = tc_configure();
-    if (e == cudaSuccess) e = tc_node_configure();
-    if (e == cudaSuccess) e = tc_layers_configure();
-    { const char* m = getenv("BDIFF_MEGA"); h->mega = !(m && m[0] == '0'); }
+    e = tc_layers_configure();
     h->tc_layer_bytes = tc_blob_bytes(d.Ed, d.Xd);
     h->tc_node_layer_bytes = tc_node_blob_bytes();
     if (e == cudaSuccess) e = h->tc_blob.ensure(h->tc_layer_bytes * d.L);
@@ -418,13 +416,13 @@ int32_t bdiff_prepare(bdiff_handle* h, void* stream) {
   return e == cudaSuccess ? BDIFF_OK : h->fail(BDIFF_ECUDA, "prepare: %s", cudaGetErrorString(e));
 }
 
-int32_t bdiff_selftest_umma(void* stream, const float* A, const float* W, float* C) {
+int32_t bdiff_selftest_split(void* stream, int32_t variant, const float* A, const float* W, float* C) {
   if (!A || !W || !C) return BDIFF_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tc_configure() != cudaSuccess) return BDIFF_ECUDA;
+  if (selftest_configure() != cudaSuccess) return BDIFF_ECUDA;
   void* img = nullptr;
-  if (cudaMalloc(&img, 2 * 320 * 128) != cudaSuccess) return BDIFF_ENOMEM;
-  launch_umma_selftest(st, A, W, static_cast<unsigned char*>(img), C);
+  if (cudaMalloc(&img, selftest_img_bytes()) != cudaSuccess) return BDIFF_ENOMEM;
+  launch_umma_selftest_split(st, A, W, static_cast<unsigned char*>(img), C, variant);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(img);
   return e == cudaSuccess ? BDIFF_OK : BDIFF_ECUDA;
@@ -503,9 +501,24 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
     node_dep[2 * u] = e1 >= e0 ? (int)(e0 / 128) : 0;
     node_dep[2 * u + 1] = e1 >= e0 ? (int)(e1 / 128) : -1;
   }
+  // per node: edge tiles strictly inside its row (their sums go through Work::mid, see edge_tile_epilogue.inc)
+  const int Npad128 = round_up(N, 128);
+  std::vector<int> node_mid((size_t)2 * Npad128, 0);
+  for (int k = 0; k < B; ++k) {
+    const long long na = act_off[k + 1] - act_off[k];
+    for (long long a = 0; a < na; ++a) {
+      const long long g0 = edge_off[k] + a * na, g1 = g0 + na - 1;
+      const long long t0 = g0 / 128, t1 = g1 / 128;
+      if (t1 - t0 >= 2) {
+        const int i = act_idx[act_off[k] + a];
+        node_mid[2 * (size_t)i] = (int)(t0 + 1);
+        node_mid[2 * (size_t)i + 1] = (int)(t1 - t0 - 1);
+      }
+    }
+  }
   const size_t o_mo = take((B + 1) * 4), o_ao = take((B + 1) * 4), o_ai = take((M + 1) * 4), o_nm = take(N * 4),
                o_eo = take((B + 1) * 8), o_tm = take((ntile128 + 1) * 4), o_mk = take(N),
-               o_ed = take((ntile128 + 1) * 8), o_nd = take((ntile32 + 1) * 8);
+               o_ed = take((ntile128 + 1) * 8), o_nd = take((ntile32 + 1) * 8), o_mid = take((size_t)Npad128 * 8);
   std::vector<unsigned char> stage(off, 0);
   memcpy(stage.data() + o_mo, mol_off.data(), (B + 1) * 4);
   memcpy(stage.data() + o_ao, act_off.data(), (B + 1) * 4);
@@ -516,6 +529,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   memcpy(stage.data() + o_mk, mk.data(), N);
   memcpy(stage.data() + o_ed, edge_dep.data(), edge_dep.size() * 4);
   memcpy(stage.data() + o_nd, node_dep.data(), node_dep.size() * 4);
+  memcpy(stage.data() + o_mid, node_mid.data(), node_mid.size() * 4);
   e = h->plan_buf.ensure(off);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->plan_buf.p, stage.data(), off, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -531,6 +545,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   p.tile_mol = reinterpret_cast<int*>(base + o_tm);
   p.mask = base + o_mk;
   p.edge_rc = nullptr;
+  p.node_mid = reinterpret_cast<const int2*>(base + o_mid);
   {
     const long long nrc = ntile128 * 128;
     e = h->rc_buf.ensure((size_t)(nrc > 0 ? nrc : 1) * sizeof(int4));
@@ -644,7 +659,7 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
   if (fork) cudaStreamWaitEvent(st, h->ev_join, 0);
   mark();
   h->launches += 4;
-  const bool fused = tensor && h->mega;
+  const bool fused = tensor;
   if (fused) {
     // all L layers in one persistent kernel (bdiff_layers_tc.cu); its queue head + completion flags are zeroed first
     LayerSched& q = h->sched;
@@ -661,19 +676,10 @@ static int32_t forward_impl(bdiff_handle* h, cudaStream_t st, const float* xh, c
     h->launches += 1;
   }
   for (int l = 0; l < d.L && !fused; ++l) {
-    if (tensor)
-      launch_edge_message_tc(st, p, d, h->layers[l],
-                             static_cast<const unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes, w, h->num_sms);
-    else
-      launch_edge_message(st, p, d, h->layers[l], w);
+    launch_edge_message(st, p, d, h->layers[l], w);
     mark();
     const bool last = (l == d.L - 1);
-    if (tensor)
-      launch_node_update_tc(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed,
-                            static_cast<const unsigned char*>(h->tc_node_blob.p) + (size_t)l * h->tc_node_layer_bytes, w,
-                            last ? 1 : 0, h->num_sms);
-    else
-      launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);
+    launch_node_update(st, p, d, h->layers[l], h->layers[last ? l : l + 1], h->embed, w, last ? 1 : 0);
     mark();
     h->launches += 2;
   }
@@ -692,7 +698,7 @@ int32_t bdiff_profile_forward(bdiff_handle* h, void* stream, const float* xh, co
   int32_t rc = forward_impl(h, st, xh, t, nullptr, nullptr, context, net_out, &ev);
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == BDIFF_OK && e != cudaSuccess) rc = h->fail(BDIFF_ECUDA, "profile sync: %s", cudaGetErrorString(e));
-  if (rc == BDIFF_OK && h->cfg.mode == BDIFF_MODE_TENSOR && h->mega && h->sched_buf.p) {
+  if (rc == BDIFF_OK && h->cfg.mode == BDIFF_MODE_TENSOR && h->sched_buf.p) {
     int flag = 0;
     cudaMemcpy(&flag, h->sched.err, sizeof(int), cudaMemcpyDeviceToHost);
     if (flag) { cudaMemset(h->sched.err, 0, sizeof(int)); rc = h->fail(BDIFF_ECUDA, "layer megakernel: a tile dependency wait timed out"); }
@@ -789,12 +795,26 @@ int32_t bdiff_check(bdiff_handle* h, void* stream) {
   if (!h) return BDIFF_EINVAL;
   cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "check: %s", cudaGetErrorString(e));
-  if (h->cfg.mode == BDIFF_MODE_TENSOR && h->mega && h->sched_buf.p && h->have_plan) {
+  if (h->cfg.mode == BDIFF_MODE_TENSOR && h->sched_buf.p && h->have_plan) {
     int flag = 0;
     e = cudaMemcpy(&flag, h->sched.err, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "check: %s", cudaGetErrorString(e));
     if (flag) { cudaMemset(h->sched.err, 0, sizeof(int)); return h->fail(BDIFF_ECUDA, "layer megakernel: a tile dependency wait timed out"); }
   }
+  return BDIFF_OK;
+}
+
+int32_t bdiff_nan_guard_count(bdiff_handle* h, void* stream, int64_t* count_host, int32_t reset) {
+  if (!h || !count_host) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
+  *count_host = 0;
+  if (!h->have_plan) return BDIFF_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int v = 0;
+  cudaError_t e = cudaMemcpyAsync(&v, h->work.nan_flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && reset) e = cudaMemsetAsync(h->work.nan_flag + 1, 0, sizeof(int), st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "nan_guard_count: %s", cudaGetErrorString(e));
+  *count_host = v;
   return BDIFF_OK;
 }
 

@@ -36,6 +36,7 @@ struct Plan {
   const int* tile_mol;   // [ceil(E/128)] molecule that contains edge 128*t (start of the linear molecule search)
   const unsigned char* mask;  // [N]
   const int4* edge_rc;   // [128*ceil(E/128)] per edge {row, col, b, nact} (row = -1 past E): b = position in the row segment
+  const int2* node_mid;  // [Npad] per node {first, count} of the 128-edge tiles that lie strictly inside its row (count > 0 only for n >= 130)
 };
 
 // Per-layer packed weights (device pointers, K-major).

@@ -1,43 +1,42 @@
-// bdiff_edge_tc.cuh — declarations shared by the tensor-core edge pass (bdiff_edge_tc.cu) and the layer megakernel
-// (bdiff_layers_tc.cu): tile / TMEM constants, shared-memory layout, the per-thread vector-channel update.
+// bdiff_edge_tc.cuh — declarations of the tensor-core edge tile of the layer megakernel (bdiff_layers_tc.cu):
+// tile / TMEM constants, shared-memory layout, weight-slab stream, the per-thread vector-channel update.
 #pragma once
 #include "bdiff_kernels.h"
-#include "bdiff_tc.cuh"
+#include "bdiff_slab.cuh"
 
 namespace bdiff {
 
-#ifndef BDIFF_STAMP
-#define BDIFF_STAMP(slot) do { if (w.dbg && (slot) < 64) w.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
-#endif
-
-constexpr int TC_THREADS = 192;
 constexpr int TMT = 128;                 // edges per tile
-constexpr int RING_STAGE = 320 * 128;    // bytes of the largest weight chunk (320 rows x 64 bf16)
-// TMEM column map (512 columns allocated)
+// weight ring: TC_NSLOT slots of TC_SLOT bytes; a chunk is one slab plane (N rows x 32 B, N <= 320) or a group of
+// small planes, always a single contiguous TMA bulk copy
+constexpr int TC_SLOT = 320 * 32;        // 10 KiB
+constexpr int TC_NSLOT = 4;
+// TMEM column map of an edge tile (512 columns allocated)
 constexpr int TM_S = 0, TM_U0 = 256, TM_U1 = 288, TM_MV = 320, TM_VD0 = 416;
+constexpr int TM_EX = 416, TM_EX_STRIDE = 40;     // pair-exchange scratch (over VD0, which is dead by then): 2 x 40 columns
 
-__host__ __device__ inline int tc_nc0(int Ed, int Xd) {          // weight chunks of message GCP 0
-  const int k0raw = Ed + (64 + Xd) / 4 + 9;
-  return ((k0raw + 15) / 16 + 3) / 4;
+__host__ __device__ inline int tc_k0_steps(int Ed, int Xd) {     // K=16 steps of message GCP 0's edge part
+  return (Ed + (64 + Xd) / 4 + 9 + 15) / 16;
+}
+// bytes of one layer's edge-pass weight stream (see k_pack_edge_slabs for the order)
+__host__ __device__ inline size_t tc_edge_stream_bytes(int Ed, int Xd) {
+  return (size_t)tc_k0_steps(Ed, Xd) * 2 * 256 * 32 + 3 * ((size_t)16 * 2 * 320 * 32 + 2 * 2 * 256 * 32) + (size_t)16 * 2 * 32 * 32;
 }
 
-// mbarriers / bookkeeping common to every tensor-core kernel of this library; first member (base class) of each
-// kernel's shared-memory tail so that the layer megakernel can overlay the edge and node tails.
+// mbarriers / bookkeeping of the megakernel; first member (base class) of both tile tails
 struct TcBars {
-  uint64_t full[2], empty[2], a_ready, d_full, wbar, u_free;
+  uint64_t full[TC_NSLOT], empty[TC_NSLOT], a_ready, d_full, wbar, u_free;
   uint64_t item_full[2], item_empty[2], tile_done;
-  int item[2][4];          // megakernel work items {type, layer, tile, -}
+  int item[2][4];          // work items {type, layer, tile, -}
   uint32_t tmem_ptr;
   uint32_t pad_;
 };
 
-// --------------------------------------------------------------------------------------------- fused kernel
 // Thread roles: warps 0-7 epilogue/compute — edge r of the tile is owned by the thread PAIR (r, r+128): "half" 0
 // works on accumulator columns [0,128) and vector channels [0,16), half 1 on columns [128,256) and channels
-// [16,32) (both warps of a pair address the same TMEM lanes: lane quarter = warp % 4); warp 8 = TMA producer
-// (+ TMEM allocator), warp 9 = MMA issuer.
+// [16,32) (both warps of a pair address the same TMEM lanes: lane quarter = warp % 4); warp 8 = scheduler + TMA
+// producer (+ TMEM allocator), warp 9 = MMA issuer.
 constexpr int TC_EPI = 256;
-constexpr int TC_THREADS2 = TC_EPI + 64;
 
 struct alignas(16) SmallW {   // fp32 copies of the thread-local (vector channel) weights, broadcast-read
   float Wd0x[16 * 20];     // [Xd][hid0]
@@ -52,16 +51,14 @@ struct alignas(16) SmallW {   // fp32 copies of the thread-local (vector channel
   float ba[4];
 };
 
-constexpr int ST_LD = 37;
-struct TcSmemTail : TcBars {
-  float sT[2][TMT][ST_LD]; // per-half transpose buffer of the final reduction; reused as the pair-exchange buffer and as
-                           // the staging area of the coalesced xi / P_j gathers
+struct EdgeTail : TcBars {
+  float2 sR[64][32];       // rows 64..127 of the reduction buffer (rows 0..63 live in A block 8, free by then)
+  float2 wbuf[8][2][32];   // per 16-row window: [0] head piece (segment entered from the previous window), [1] tail / whole piece
   SmallW sw;
   float sAttn[2][TMT];
   int sRow[TMT], sCol[TMT], sB[TMT], sNa[TMT];
+  uint32_t winfo[8];       // per window: start mask | end mask << 16
 };
-
-constexpr size_t TC_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)RING_STAGE + sizeof(TcSmemTail) + 1024;
 
 // Gate of the previous GCP from TMEM (U), vector-message update in TMEM scratch for this thread's 16 channels,
 // and this thread's partial vector_down / vector_down_frames sums of the NEXT GCP.
@@ -99,8 +96,8 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {          // two output channels (j = 2jp, 2jp+1) per packed instruction
       const int o = oc * 8 + 2 * jp;
-      const float2 g = sigmoid_fast2(__fadd2_rn(make_float2(u[2 * jp], u[2 * jp + 1]),
-                                                *reinterpret_cast<const float2*>(bgp + o)));
+      const float2 g = sigmoid_acc2(__fadd2_rn(make_float2(u[2 * jp], u[2 * jp + 1]),
+                                               *reinterpret_cast<const float2*>(bgp + o)));
       float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0;
 #pragma unroll
       for (int h = 0; h < HP; ++h) {
@@ -152,5 +149,23 @@ __device__ __forceinline__ void gate_update(uint32_t tl, int half, int ucol, con
   tmem_st_wait();
 }
 
+// The two threads of a pair (same TMEM lane) swap their 33 partial sums through TMEM scratch columns: no shared memory.
+// Callers guarantee that nobody still reads the columns (VD0) being overwritten.
+__device__ __forceinline__ void pair_exchange33(uint32_t tl, int half, const float* __restrict__ mine, float* __restrict__ theirs) {
+  float pad[40];
+#pragma unroll
+  for (int i = 0; i < 33; ++i) pad[i] = mine[i];
+#pragma unroll
+  for (int i = 33; i < 40; ++i) pad[i] = 0.f;
+  tmem_st8xN<5>(tl + TM_EX + half * TM_EX_STRIDE, pad);
+  tmem_st_wait();
+  tc_fence_before();
+  named_bar_sync(3, TC_EPI);
+  tc_fence_after();
+  float got[40];
+  tmem_ld8xN<5>(tl + TM_EX + (half ^ 1) * TM_EX_STRIDE, got);
+#pragma unroll
+  for (int i = 0; i < 33; ++i) theirs[i] = got[i];
+}
 
 }  // namespace bdiff

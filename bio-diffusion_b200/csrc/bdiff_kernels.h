@@ -23,11 +23,12 @@ struct Work {
                    //             edges of a tile have consecutive target nodes -> coalesced per-edge gather), else nullptr
   int npad;        // row count of the padded node buffers
   float* agg;      // [N,352] aggregated messages
+  float* mid;      // [ceil(E/128),352] tensor mode: message sums of edge tiles that lie strictly inside one source node's row
   float* hproj;    // [N,32]  projected scalar outputs (Hin used)
   float* e;        // [E,Ed]
   float* xi;       // [E,Xd*3]
   float* frames;   // [E,9]
-  int* nan_flag;
+  int* nan_flag;   // [0] NaN seen in this forward (gcpnet.py:1214-1216 guard), [1] forwards in which the guard fired (cumulative)
   long long* dbg;  // optional [CTA][64] clock64 stamps of the tensor-core kernels (BDIFF_TIMING=1), else nullptr
 };
 
@@ -52,20 +53,13 @@ void launch_edge_rc(cudaStream_t st, const Plan& p, int4* out, long long n);
 void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
                  int kpad, int nout);
 
-// tensor-core edge pass (bdiff_edge_tc.cu)
-cudaError_t tc_configure();
+// tensor mode: per-layer split-bf16 weight streams (bdiff_tc_pack.cu)
 bool tc_supported(int Ed, int Xd);
 size_t tc_blob_bytes(int Ed, int Xd);
-void launch_tc_pack(cudaStream_t st, const LayerW& lw, const Dims& d, unsigned char* blob);
-void launch_edge_message_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const unsigned char* blob,
-                            const Work& w, int num_sms);
-// tensor-core node pass (bdiff_node_tc.cu)
-cudaError_t tc_node_configure();
 size_t tc_node_blob_bytes();
+void launch_tc_pack(cudaStream_t st, const LayerW& lw, const Dims& d, unsigned char* blob);
 void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
                          unsigned char* blob);
-void launch_node_update_tc(cudaStream_t st, const Plan& p, const Dims& d, const LayerW& lw, const LayerW& wn,
-                           const EmbedW& ew, const unsigned char* blob, const Work& w, int last, int num_sms);
 // all layers in one persistent kernel (bdiff_layers_tc.cu)
 struct LayerSched {
   const LayerW* layers;            // [L] device copy of the per-layer weight pointer tables
@@ -83,6 +77,9 @@ struct LayerSched {
 cudaError_t tc_layers_configure();
 void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerSched& q,
                       const Work& w, int num_sms);
-void launch_umma_selftest(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
+cudaError_t selftest_configure();
+size_t selftest_img_bytes();
+void launch_umma_selftest_split(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C,
+                                int variant);
 
 }  // namespace bdiff

@@ -775,6 +775,7 @@ __global__ void __launch_bounds__(128) k_finalize(Plan p, Dims d, Work w, float*
   const int k = blockIdx.x;
   const int n0 = p.mol_off[k], n1 = p.mol_off[k + 1];
   const bool bad = (*w.nan_flag) != 0;
+  if (bad && k == 0 && threadIdx.x == 0) atomicAdd(w.nan_flag + 1, 1);     // cumulative NaN-guard hits (bdiff_nan_guard_count)
   float s[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = n0 + threadIdx.x; i < n1; i += 128) {
     const float m = p.mask[i] ? 1.f : 0.f;

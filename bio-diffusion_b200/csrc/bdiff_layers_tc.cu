@@ -32,12 +32,14 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Shared memory: [A region: 9 x 16 KiB (edge tile: hi blocks 0-3, lo blocks 4-7, extra block 8; node tile: 5 R5 blocks
+// of 20 KiB + NodeScratch)] [weight ring: TC_NSLOT x 10 KiB] [tail: barriers + per-tile small weights / buffers].
 union LayersTail {
   TcBars bars;
-  TcSmemTail edge;
-  NodeR4Tail node;
+  EdgeTail edge;
+  NodeTail node;
 };
-constexpr size_t LAYERS_SMEM_BYTES = 5 * (size_t)X_BLOCK + 2 * (size_t)RING_STAGE + sizeof(LayersTail) + 1024;
+constexpr size_t LAYERS_SMEM_BYTES = XE_BLOCKS * (size_t)X_BLOCK + TC_NSLOT * (size_t)TC_SLOT + sizeof(LayersTail) + 1024;
 static_assert(LAYERS_SMEM_BYTES <= 232448, "shared memory budget of the layer megakernel");
 
 // 12 warps: 0-7 compute (two warpgroups), 8 scheduler + TMA producer, 9 MMA issuer, 10-11 padding so that the
@@ -54,15 +56,13 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
   constexpr int H2 = HID0 / 2;
   constexpr int K0RAW = ED + HID0 + 9;
   constexpr int K0S = (K0RAW + 15) / 16;
-  constexpr int NC0 = (K0S + 3) / 4;
-  constexpr int NSTRIDE = RING_STAGE;       // node-pass weight chunks use the edge pass's (larger) ring stages here
   static_assert(HID0 % 2 == 0 && H2 * 3 <= 32 && HID0 + 9 <= 32 && ED % 16 == 0, "layout");
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* X = smem;
-  unsigned char* ring = smem + 5 * X_BLOCK;
-  unsigned char* tail = ring + 2 * RING_STAGE;
+  unsigned char* ring = smem + XE_BLOCKS * X_BLOCK;
+  unsigned char* tail = ring + TC_NSLOT * TC_SLOT;
   TcBars& B = *reinterpret_cast<TcBars*>(tail);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hid0 = d.hid0;
@@ -71,10 +71,8 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
   int* const flags = q.sched + 2;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&B.full[i], 1); mbar_init(&B.empty[i], 1);
-      mbar_init(&B.item_full[i], 1); mbar_init(&B.item_empty[i], TC_EPI + 1);
-    }
+    for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&B.full[i], 1); mbar_init(&B.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&B.item_full[i], 1); mbar_init(&B.item_empty[i], TC_EPI + 1); }
     mbar_init(&B.tile_done, TC_EPI);
     mbar_init(&B.a_ready, TC_EPI);
     mbar_init(&B.d_full, 1);
@@ -106,12 +104,21 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         B.item[slot][0] = type; B.item[slot][1] = layer; B.item[slot][2] = tile;
         mbar_arrive(&B.item_full[slot]);
         if (type < 0) break;
+        const unsigned char* blob = type == 0 ? q.edge_blob + (size_t)layer * q.edge_blob_stride
+                                              : q.node_blob + (size_t)layer * q.node_blob_stride;
+        size_t off = 0;
+        auto push = [&](uint32_t bytes) {
+          const uint32_t s = ci % TC_NSLOT;
+          mbar_wait_backoff(&B.empty[s], ((ci / TC_NSLOT) & 1) ^ 1);
+          mbar_expect_tx(&B.full[s], bytes);
+          bulk_g2s(ring + s * TC_SLOT, blob + off, bytes, &B.full[s]);
+          off += bytes;
+          ++ci;
+        };
         if (type == 0) {
-          const unsigned char* blob = q.edge_blob + (size_t)layer * q.edge_blob_stride;
 #include "edge_tile_producer.inc"
         } else {
           const int last = layer == q.L - 1;
-          const unsigned char* blob = q.node_blob + (size_t)layer * q.node_blob_stride;
 #include "node_r4_tile_producer.inc"
         }
       }
@@ -125,44 +132,47 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
                      i32n = umma_idesc_bf16(32, true);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0, pu = 0;
-      int ms = 28;
       auto wait_a = [&]() { mbar_wait_backoff(&B.a_ready, pa); pa ^= 1; tc_fence_after(); };
       auto wait_w = [&]() -> uint32_t {
-        const uint32_t s = ci & 1;
-        mbar_wait_backoff(&B.full[s], (ci >> 1) & 1);
+        const uint32_t s = ci % TC_NSLOT;
+        mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
         tc_fence_after();
-        return raddr + s * RING_STAGE;
+        return raddr + s * TC_SLOT;
       };
-      auto done_w = [&]() { umma_commit(&B.empty[ci & 1]); ++ci; };
+      auto done_w = [&]() { umma_commit(&B.empty[ci % TC_NSLOT]); ++ci; };
       auto commit_d = [&]() { umma_commit(&B.d_full); };
-      auto gemm256 = [&](bool fresh, uint32_t dcol = NM_S) {
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t wb = wait_w();
-          for (int s = 0; s < 4; ++s)
-            umma_bf16(tmem + dcol, umma_desc_sw128(xaddr + j * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256,
-                      fresh ? (j | s) > 0 : true);
-          done_w();
-        }
-      };
-      auto gemm288 = [&](bool fresh_s, bool negate_u) {
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t wb = wait_w();
-          for (int s = 0; s < 4; ++s) {
-            const uint64_t ad = umma_desc_sw128(xaddr + j * X_BLOCK + s * 32);
-            umma_bf16(tmem + NM_S, ad, umma_desc_sw128(wb + s * 32), i256, fresh_s ? (j | s) > 0 : true);
-            umma_bf16(tmem + NM_U, ad, umma_desc_sw128(wb + 256 * 128 + s * 32), negate_u ? i32n : i32,
-                      negate_u ? (j | s) > 0 : true);
+      // node-tile GEMMs over A blocks 0..3 (R5 layout: views at row 0 and row 32, four products per K step).
+      // N = 256 or 288 plane rows; the 32 rows behind the first 256 go to U: umode 1 accumulates, 2 starts fresh and negated
+      auto ngemm = [&](int N, uint32_t dcol, bool fresh, int umode) {
+        for (int ks = 0; ks < 16; ++ks) {
+          const uint32_t a = xaddr + (ks >> 2) * R5_BLOCK + (ks & 3) * 32;
+          const uint64_t v0 = umma_desc_sw128(a), v1 = umma_desc_sw128(a + 4096);
+          for (int pl = 0; pl < 2; ++pl) {                   // hi plane, lo plane
+            const uint32_t wb = wait_w();
+            const bool first = ks == 0 && pl == 0;
+            umma_bf16(tmem + dcol, v0, umma_desc_k16(wb, N * 16, 128), i256, fresh ? !first : true);
+            umma_bf16(tmem + dcol, v1, umma_desc_k16(wb, N * 16, 128), i256, true);
+            if (umode) {
+              const uint64_t bu = umma_desc_k16(wb + 256 * 16, N * 16, 128);
+              umma_bf16(tmem + NM_U, v0, bu, umode == 2 ? i32n : i32, umode == 2 ? !first : true);
+              umma_bf16(tmem + NM_U, v1, bu, umode == 2 ? i32n : i32, true);
+            }
+            done_w();
           }
-          done_w();
         }
       };
-      auto gemm_extra = [&]() {
-        const uint32_t wb = wait_w();
-        for (int s = 0; s < 2; ++s)
-          umma_bf16(tmem + NM_S, umma_desc_sw128(xaddr + 4 * X_BLOCK + s * 32), umma_desc_sw128(wb + s * 32), i256, true);
-        done_w();
+      auto nextra = [&]() {                                  // += [vn | q] (block 4, 32 columns) . W[:, 256:288]
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t a = xaddr + 4 * R5_BLOCK + ks * 32;
+          const uint64_t v0 = umma_desc_sw128(a), v1 = umma_desc_sw128(a + 4096);
+          for (int pl = 0; pl < 2; ++pl) {
+            const uint32_t wb = wait_w();
+            umma_bf16(tmem + NM_S, v0, umma_desc_k16(wb, 256 * 16, 128), i256, true);
+            umma_bf16(tmem + NM_S, v1, umma_desc_k16(wb, 256 * 16, 128), i256, true);
+            done_w();
+          }
+        }
       };
-      (void)ms;
       for (uint32_t k = 0;; ++k) {
         const uint32_t slot = k & 1;
         mbar_wait_backoff(&B.item_full[slot], (k >> 1) & 1);
@@ -186,11 +196,9 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
     // ============================================================================ compute / epilogue warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_COMPUTE));
     uint32_t pd = 0, pw = 0;
-    int es = 64;                 // the per-tile bodies' own stamps are off here; this kernel stamps per item (below)
     int cur_type = -1, cur_layer = -1;
     auto wait_d = [&]() { mbar_wait(&B.d_full, pd); pd ^= 1; tc_fence_after(); };
     auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&B.a_ready); };
-    (void)es;
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
     for (uint32_t k = 0;; ++k) {
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         if (tid == 0) {
           const LayerW lw = q.layers[layer];       // by value: the pointer loads go out together, not one per copy
           if (type == 0) {
-            SmallW& s = reinterpret_cast<TcSmemTail*>(tail)->sw;
+            SmallW& s = reinterpret_cast<EdgeTail*>(tail)->sw;
             mbar_expect_tx(&B.wbar, sz(XD * HID0) + sz(XD * 3) + sz(HID0 * 32) +
                                         3 * (sz(256) + sz(256) + sz(256) + sz(96) + sz(32)) + sz(32) + sz(256) + sz(1));
             auto cp = [&](float* dst, const float* src, int n) { bulk_g2s(dst, src, sz(n), &B.wbar); };
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
           } else {
             const int last = layer == q.L - 1;
             const LayerW wn = q.layers[last ? layer : layer + 1];
-            SmallWR4& s = reinterpret_cast<NodeR4Tail*>(tail)->sw;
+            SmallWR4& s = reinterpret_cast<NodeTail*>(tail)->sw;
             uint32_t total = sz(1024) + sz(192) + sz(512) + sz(32) + 2 * sz(256) + sz(256) + sz(96) + sz(8) + 2 * sz(256) + sz(1);
             total += last ? sz(1024) + sz(96) + sz(d.Hin) : sz(256) + 2 * sz(32 * hid0) + 2 * sz(96);
             mbar_expect_tx(&B.wbar, total);
@@ -262,7 +270,10 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         const long long t0 = clock64();
         for (int u = lo; u <= hi; ++u) {
           while (ld_acquire_gpu(fbase + u) == 0) {
-            if (clock64() - t0 > (1ll << 31)) { atomicExch(q.err, 1); break; }
+            // every producer precedes its consumer in the claim order and all CTAs are resident, so this wait is bounded
+            // by a few tile times; > 2^32 cycles (~2 s) can only mean a broken schedule: record it and abort the kernel
+            // HERE (sticky launch failure) rather than computing on stale data
+            if (clock64() - t0 > (1ll << 32)) { atomicExch(q.err, 1); __threadfence_system(); __trap(); }
           }
         }
       }
@@ -270,14 +281,13 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
       __threadfence();
       if (tid == 0 && w.dbg && k < 16) w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 2] = clock64();
       if (type == 0) {
-        TcSmemTail& T = *reinterpret_cast<TcSmemTail*>(tail);
+        EdgeTail& T = *reinterpret_cast<EdgeTail*>(tail);
         const int half = tid >> 7, r = tid & 127;
         const SmallW& sw = T.sw;
-        float* exch_mine = &T.sT[half][r][0];
-        const float* exch_other = &T.sT[half ^ 1][r][0];
 #include "edge_tile_epilogue.inc"
       } else {
-        NodeR4Tail& T = *reinterpret_cast<NodeR4Tail*>(tail);
+        NodeTail& T = *reinterpret_cast<NodeTail*>(tail);
+        NodeScratch& SC = *reinterpret_cast<NodeScratch*>(X + R5_BLOCKS * R5_BLOCK);
         const int last = layer == q.L - 1;
         const int l = lane, s = warp, c0 = warp * 32;
         const SmallWR4& sw = T.sw;
@@ -295,6 +305,8 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
+
+bool tc_supported(int Ed, int Xd) { return (Ed == 64 && Xd == 16) || (Ed == 16 && Xd == 8); }
 
 cudaError_t tc_layers_configure() {
   cudaError_t e = cudaFuncSetAttribute(k_layers_tc<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,28 +1,26 @@
-// bdiff_node_tc.cuh — declarations shared by the tensor-core node pass (bdiff_node_tc.cu) and the layer megakernel
-// (bdiff_layers_tc.cu).
+// bdiff_node_tc.cuh — declarations of the tensor-core node tile of the layer megakernel (bdiff_layers_tc.cu).
+//
+// Tile = 32 nodes.  The A operand uses the "R5" split-bf16 layout of bdiff_slab.cuh (each node row stored as
+// hi, lo, hi, lo, hi; two 128-row views and four products per K step), which leaves node l's complete accumulator row
+// in all four TMEM lane quarters: the 8 compute warps share the same 32 nodes, warp s owns accumulator columns
+// [32 s, 32 s + 32) (reachable in its own lane quarter) and 1/8 of the vector-channel work.
 #pragma once
 #include "bdiff_edge_tc.cuh"
 
 namespace bdiff {
 
 constexpr int NT_EPI = 256;
-constexpr int NT_THREADS = NT_EPI + 64;
-constexpr int NTM = 128;
-constexpr int NRING = 288 * 128;
-constexpr int NSTAGES = 2;
-constexpr int NM_S = 0, NM_U = 256, NM_CHI = 288, NM_VDF = 384, NM_EX = 432;
-
-struct alignas(16) SmallWN {
-  float Wdf[64 * 16], Wff[64 * 3], Wuf[16 * 32], bgf[32];
-  float b1[256], b2[256];
-  float Wdp[32 * 8], Wfp[32 * 3], Wup[8], bp[256], wgp[256], bgp[4];
-  float b0[256];
-  float Wd0i[32 * 20], Wd0j[32 * 20], Wf0i[32 * 3], Wf0j[32 * 3];
-  float pWd[32 * 32], pWf[32 * 3], pbs[32];
-};
-
+constexpr int NM_S = 0, NM_U = 256;
 constexpr int R4M = 32;
-constexpr int NM_S1 = 256;        // second accumulator of the row-replicated kernel (overlaps U, see G4)
+constexpr int NM_S1 = 256;        // second accumulator (overlaps U, see G4)
+
+// bytes of one layer's node-pass weight stream (see k_pack_node_slabs for the order)
+__host__ __device__ inline size_t tc_node_stream_bytes(int last) {
+  const size_t s256 = 2 * 256 * 32, s288 = 2 * 288 * 32, s32 = 2 * 32 * 32;
+  size_t b = 16 * s256 + 16 * s288 + 2 * s256 + 16 * s256 + 16 * s288;      // G1a G1b G1c G2 G3a
+  b += last ? 2 * s256 + 19 * s32 : 16 * s256 + 2 * s256 + 16 * s256;       // G3b Gp | G4 G3b G5
+  return b;
+}
 
 // the small weights with the (mutually exclusive) next-layer / projection sets overlaid
 struct alignas(16) SmallWR4 {
@@ -35,28 +33,20 @@ struct alignas(16) SmallWR4 {
   } u;
 };
 
-struct NodeR4Tail : TcBars {
+struct NodeTail : TcBars {
   SmallWR4 sw;
+};
+
+// scratch of a node tile; lives behind the 5 R5 blocks inside the (larger) A region of the edge tile
+struct NodeScratch {
   float4 sT[8][8 * 8];     // per-warp 8 x 32 fp32 transposition scratch (xor-swizzled 16-byte chunks)
   float sV[R4M][193];      // per node [agg_v (32x3) | chi (32x3)]; chi is replaced by chi_new in E3a
   float sVD[R4M][49];      // vector_down of the feed-forward GCP (16 x 3)
   float sVP[R4M][25];      // vector_down of the position GCP (8 x 3)
   float sDot[8][R4M];
+  int2 sMid[R4M];          // per node {first middle edge tile, count} of its row (n > 128 only), see Plan::node_mid
 };
-constexpr size_t R4_SMEM_BYTES = 5 * (size_t)X_BLOCK + NSTAGES * (size_t)NRING + sizeof(NodeR4Tail) + 1024;
-
-__device__ __forceinline__ void x_store8_rep4(unsigned char* X, int l, int kk, const float* v) {   // kk % 8 == 0
-  const uint4 u = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  unsigned char* q = X + (kk >> 6) * X_BLOCK + sw128_offset(l, kk & 63);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(q + k * 4096) = u;
-}
-__device__ __forceinline__ void x_store1_rep4(unsigned char* X, int l, int kk, float v) {
-  const __nv_bfloat16 b = __float2bfloat16_rn(v);
-  unsigned char* q = X + (kk >> 6) * X_BLOCK + sw128_offset(l, kk & 63);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) *reinterpret_cast<__nv_bfloat16*>(q + k * 4096) = b;
-}
+static_assert(R5_BLOCKS * (size_t)R5_BLOCK + sizeof(NodeScratch) <= XE_BLOCKS * (size_t)X_BLOCK, "node scratch must fit behind the R5 blocks");
 
 // Global <-> "lane = row" register tiles through the per-warp scratch, so that every global instruction touches 4
 // rows x 128 contiguous bytes instead of 32 rows x 16 bytes (the L1 processes one line tag per cycle).

@@ -188,6 +188,61 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(h);
 }
 
+
+// 64-bit UMMA shared-memory descriptor for a K-major operand WITHOUT swizzle ("interleaved" canonical layout,
+// cute UMMA::LayoutType::SWIZZLE_NONE): core matrices of 8 rows x 16 bytes are contiguous (128 B); consecutive
+// 8-row groups are `sbo` bytes apart, the two 16-byte K chunks of one K=16 step are `lbo` bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_k16(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------- split-bf16 operands
+// Every GEMM operand of the tensor path is the pair (hi, lo) of bf16 numbers with hi = RN_bf16(value)
+// and lo = RN_bf16(value - hi): hi + lo carries >= 16 significant bits (relative error
+// <= 2^-18) and is exactly representable in fp32.  A product is evaluated as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
+// (three tcgen05 MMAs accumulating into the same fp32 TMEM columns; the dropped A_lo.W_lo term is 2^-18 relative).
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 join_bf16x2(uint32_t hi, uint32_t lo) {
+  return make_float2(__uint_as_float(hi << 16) + __uint_as_float(lo << 16),
+                     __uint_as_float(hi & 0xffff0000u) + __uint_as_float(lo & 0xffff0000u));
+}
+__device__ __forceinline__ void split_bf16(float a, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(a);
+  lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+}
+
+// fp32-class activations for the tensor path: ex2.approx / rcp.approx are accurate to ~2 ulp (the former
+// tanh.approx form was good to 2^-11 only).  sigmoid(x) = 1 / (1 + 2^(-x log2 e)).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float silu_acc(float x) { return x * sigmoid_acc(x); }
+__device__ __forceinline__ float2 sigmoid_acc2(float2 x) {
+  const float2 t = __fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+  return make_float2(rcp_approx(d.x), rcp_approx(d.y));
+}
+__device__ __forceinline__ float2 silu_acc2(float2 x) { return __fmul2_rn(x, sigmoid_acc2(x)); }
+
 // A-operand tile: 128 rows x 64 bf16 per K-block (16 KiB), K-blocks consecutive.
 constexpr int X_BLOCK = 128 * 128;
 __device__ __forceinline__ void x_store8(unsigned char* X, int r, int kk, const float* v) {   // kk % 8 == 0

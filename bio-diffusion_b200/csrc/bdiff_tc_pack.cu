@@ -1,0 +1,116 @@
+// bdiff_tc_pack.cu — per-layer weight streams of the tensor path: split-bf16 K=16 slabs (bdiff_slab.cuh) in exactly the
+// order the megakernel's TMA lane streams them.  Runs once per weight update (bdiff_prepare).
+#include "bdiff_node_tc.cuh"
+
+namespace bdiff {
+
+size_t tc_blob_bytes(int Ed, int Xd) { return tc_edge_stream_bytes(Ed, Xd); }
+size_t tc_node_blob_bytes() { return tc_node_stream_bytes(0); }      // the last layer's stream is shorter
+
+// Edge pass:  G0: K0S steps x N=256 (W0e, zero-padded to K0S*16 rows)
+//             for k = 1..3:  16 steps x N=320 ([W_k[:, :256] | Wg_{k-1} | Wg_k]),  2 steps x N=256 (W_k rows 256..287)
+//             G4: 16 steps x N=32 (Wg_3)
+// one thread per (plane row, k in [0,16)); writes the hi and the lo plane element
+__global__ void k_pack_edge_slabs(LayerW lw, Dims d, unsigned char* __restrict__ blob) {
+  const int K0S = tc_k0_steps(d.Ed, d.Xd);
+  const long long rows_g = 16 * 320 + 2 * 256;
+  const long long total_rows = (long long)K0S * 256 + 3 * rows_g + 16 * 32;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_rows * 16) return;
+  long long row = idx >> 4;
+  const int kk = (int)(idx & 15);
+  size_t base = 0;
+  int N, n, k;
+  float v;
+  if (row < (long long)K0S * 256) {
+    const int step = (int)(row / 256);
+    n = (int)(row % 256); N = 256; base = (size_t)step * 2 * 256 * 32; k = step * 16 + kk;
+    v = k < d.K0 ? lw.W0e[(size_t)k * 256 + n] : 0.f;
+  } else {
+    row -= (long long)K0S * 256;
+    base = (size_t)K0S * 2 * 256 * 32;
+    const size_t bytes_g = (size_t)16 * 2 * 320 * 32 + 2 * 2 * 256 * 32;
+    if (row < 3 * rows_g) {
+      const int gi = (int)(row / rows_g);
+      long long rr = row - gi * rows_g;
+      base += gi * bytes_g;
+      if (rr < 16 * 320) {
+        const int step = (int)(rr / 320);
+        n = (int)(rr % 320); N = 320; base += (size_t)step * 2 * 320 * 32; k = step * 16 + kk;
+        if (n < 256) v = lw.Wk[gi][(size_t)k * 256 + n];
+        else if (n < 288) v = (gi == 0 ? lw.Wg0 : lw.Wgk[gi - 1])[(size_t)k * 32 + (n - 256)];
+        else v = lw.Wgk[gi][(size_t)k * 32 + (n - 288)];
+      } else {
+        rr -= 16 * 320;
+        const int step = (int)(rr / 256);
+        n = (int)(rr % 256); N = 256; base += (size_t)16 * 2 * 320 * 32 + (size_t)step * 2 * 256 * 32; k = 256 + step * 16 + kk;
+        v = k < kKM ? lw.Wk[gi][(size_t)k * 256 + n] : 0.f;
+      }
+    } else {
+      row -= 3 * rows_g;
+      base += 3 * bytes_g;
+      const int step = (int)(row / 32);
+      n = (int)(row % 32); N = 32; base += (size_t)step * 2 * 32 * 32; k = step * 16 + kk;
+      v = lw.Wgk[2][(size_t)k * 32 + n];
+    }
+  }
+  slab_store(blob + base, N, n, kk, v);
+}
+
+// Node pass (issue order):  G1a 16x256: W1[0:256]   | G1b 16x288: W1[256:512] + Wg_ff | G1c 2x256: W1[512:544]
+//                           G2 16x256: W2           | G3a 16x288: Wp[0:256] + Wg_ff   |
+//   not last: G4 16x256: next.Wsi | G3b 2x256: Wp[256:288] | G5 16x256: next.Wsj
+//   last:     G3b 2x256           | Gp 19x32: projection scalar_out (K = 300 -> 304, Hin -> 32 rows, zero padded)
+__global__ void k_pack_node_slabs(LayerW lw, LayerW wn, EmbedW ew, Dims d, int last, unsigned char* __restrict__ blob) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long row = idx >> 4;
+  const int kk = (int)(idx & 15);
+  size_t base = 0;
+  int N = 0, n = 0, k = 0;
+  float v = 0.f;
+  bool found = false;
+  // segment walker: `steps` K steps of N-row planes; returns true if `row` falls inside, setting (n, k) and base
+  auto seg = [&](int steps, int NN) -> bool {
+    if (found) return false;
+    const long long rows = (long long)steps * NN;
+    if (row < rows) {
+      const int step = (int)(row / NN);
+      n = (int)(row % NN); N = NN; base += (size_t)step * 2 * NN * 32; k = step * 16 + kk;
+      found = true;
+      return true;
+    }
+    row -= rows;
+    base += (size_t)steps * 2 * NN * 32;
+    return false;
+  };
+  if (seg(16, 256)) v = lw.W1[(size_t)k * 256 + n];
+  else if (seg(16, 288)) v = n < 256 ? lw.W1[(size_t)(256 + k) * 256 + n] : lw.Wgf[(size_t)k * 32 + (n - 256)];
+  else if (seg(2, 256)) v = 512 + k < kKFF ? lw.W1[(size_t)(512 + k) * 256 + n] : 0.f;
+  else if (seg(16, 256)) v = lw.W2[(size_t)k * 256 + n];
+  else if (seg(16, 288)) v = n < 256 ? lw.Wp[(size_t)k * 256 + n] : lw.Wgf[(size_t)k * 32 + (n - 256)];
+  else if (!last) {
+    if (seg(16, 256)) v = wn.Wsi[(size_t)k * 256 + n];
+    else if (seg(2, 256)) v = 256 + k < kKM ? lw.Wp[(size_t)(256 + k) * 256 + n] : 0.f;
+    else if (seg(16, 256)) v = wn.Wsj[(size_t)k * 256 + n];
+  } else {
+    if (seg(2, 256)) v = 256 + k < kKM ? lw.Wp[(size_t)(256 + k) * 256 + n] : 0.f;
+    else if (seg(19, 32)) v = (k < 300 && n < d.Hin) ? ew.pWs[(size_t)k * d.Hin + n] : 0.f;
+  }
+  if (!found) return;
+  slab_store(blob + base, N, n, kk, v);
+}
+
+void launch_tc_pack(cudaStream_t st, const LayerW& lw, const Dims& d, unsigned char* blob) {
+  const long long rows = (long long)tc_k0_steps(d.Ed, d.Xd) * 256 + 3 * (16 * 320 + 2 * 256) + 16 * 32;
+  const long long total = rows * 16;
+  k_pack_edge_slabs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lw, d, blob);
+}
+
+void launch_tc_pack_node(cudaStream_t st, const LayerW& lw, const LayerW& wn, const EmbedW& ew, const Dims& d, int last,
+                         unsigned char* blob) {
+  const long long rows = 16 * 256 + 16 * 288 + 2 * 256 + 16 * 256 + 16 * 288 + (last ? 2 * 256 + 19 * 32 : 16 * 256 + 2 * 256 + 16 * 256);
+  const long long total = rows * 16;
+  k_pack_node_slabs<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(lw, wn, ew, d, last, blob);
+}
+
+}  // namespace bdiff

@@ -83,10 +83,11 @@ BDIFF_API int32_t bdiff_weights_missing(const bdiff_handle* h);
  * kernels runs inside a captured CUDA graph.  Idempotent. */
 BDIFF_API int32_t bdiff_prepare(bdiff_handle* h, void* stream);
 
-/* Hardware self test of the tcgen05 machinery the tensor mode relies on (descriptors, 128B swizzle, TMA bulk
- * copy, TMEM load/store): C[128,328] <- [A W^T (320 cols; the last 32 negated) | scratch round trip (8 cols)]
- * for A fp32[128,128], W fp32[320,128] (device pointers, rounded to bf16 inside).  Synchronises. */
-BDIFF_API int32_t bdiff_selftest_umma(void* stream, const float* A, const float* W, float* C);
+/* Hardware self test of the split-bf16 machinery of the tensor mode (csrc/bdiff_selftest.cu): hi/lo A blocks,
+ * un-swizzled K=16 weight slabs, three (variant bit 1: four, node-tile row views) products per K step, TMEM pair
+ * exchange.  C[128,336] <- [A W^T (320 cols; the last 32 negated) | exchange (16 cols)] for A fp32[128,128],
+ * W fp32[320,128] (device pointers).  variant bit 0 swaps LBO/SBO (must then FAIL the comparison).  Synchronises. */
+BDIFF_API int32_t bdiff_selftest_split(void* stream, int32_t variant, const float* A, const float* W, float* C);
 
 /* Replaces: GCPNetDynamics.get_fully_connected_edge_index (gcpnet.py:1054-1066) — as an implicit plan.
  * batch_index int64[N] (sorted molecule ids, as every caller provides), mask uint8[N].  Builds the
@@ -196,6 +197,11 @@ BDIFF_API int32_t bdiff_check_stability(void* stream, const float* x, const int3
                                         const float* bonds3, float margin1, float margin2, float margin3,
                                         const uint32_t* allowed_mask, int32_t limit_bonds_to_one, int32_t* nr_bonds,
                                         int32_t* nr_stable, int32_t* mol_stable);
+
+/* Replaces: the warn-and-zero NaN guard of gcpnet.py:1214-1216 as an observable.  *count_host <- number of denoiser
+ * forwards (since the last reset / re-plan of the workspace) in which a NaN position appeared and `vel` was zeroed.
+ * Synchronises `stream`.  bench.py reports it for every timed chain. */
+BDIFF_API int32_t bdiff_nan_guard_count(bdiff_handle* h, void* stream, int64_t* count_host, int32_t reset);
 
 /* Counters for bench.py: kernels launched by this handle since creation. */
 BDIFF_API int64_t bdiff_launch_count(const bdiff_handle* h);
