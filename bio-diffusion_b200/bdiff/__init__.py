@@ -15,6 +15,7 @@ from .sampler import GCDMSampler
 from .loss import GCDMEvalNLL, GCDMTrainLoss
 from .optim import GCDMTrainTail
 from .stability import check_molecular_stability_batch
+from .datasets import QM9_N_NODES, GEOM_N_NODES, sample_num_nodes
 from ._lib import BdiffError, load as load_library
 
-__all__ = ["DenoiserConfig", "parameter_shapes", "GCPNetDynamicsB200", "GCDMSampler", "GCDMEvalNLL", "GCDMTrainLoss", "GCDMTrainTail", "check_molecular_stability_batch", "BdiffError", "load_library"]
+__all__ = ["DenoiserConfig", "parameter_shapes", "GCPNetDynamicsB200", "GCDMSampler", "GCDMEvalNLL", "GCDMTrainLoss", "GCDMTrainTail", "check_molecular_stability_batch", "QM9_N_NODES", "GEOM_N_NODES", "sample_num_nodes", "BdiffError", "load_library"]

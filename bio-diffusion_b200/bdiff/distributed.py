@@ -8,8 +8,7 @@ reference run on rank r's sub-batch (what a user sharding the reference by hand 
 
 Training (config 5) is plain replica data parallelism in the reference (Lightning DDP, one all-reduce of all gradients
 per step, configs/trainer/ddp.yaml); `allreduce_mean_` below is that exchange for a list of gradient tensors: packed
-into buckets, ONE collective per bucket, averaged, unpacked in place.  (The CUDA backward that would feed it is not
-built yet; the helper is exercised on CPU/gloo and works unchanged over NCCL.)
+into buckets, ONE collective per bucket, averaged, unpacked in place.  
 """
 from __future__ import annotations
 
@@ -61,20 +60,52 @@ def gather_results(local_out: torch.Tensor, local_mols: Sequence[int], num_nodes
     return out
 
 
+_rank_seed_folded = False
+
+
+def decorrelate_rank_rng(rank: int) -> None:
+    """Fold the rank into this process's default CUDA generator ONCE.  The reference seeds every process identically
+    (`seed_everything(cfg.seed)`); with LPT giving equal-shaped shards for uniform-size batches, identically seeded
+    ranks would draw the same noise and generate bit-identical molecules (silent duplicates in uniqueness / novelty
+    statistics).  Rank 0 keeps the caller's stream, so a 1-GPU run is unchanged."""
+    global _rank_seed_folded
+    if _rank_seed_folded or rank == 0 or not torch.cuda.is_available():
+        _rank_seed_folded = True
+        return
+    torch.cuda.manual_seed((torch.cuda.initial_seed() + 0x9E3779B97F4A7C15 * rank) % (1 << 63))
+    _rank_seed_folded = True
+
+
 def sample_sharded(sampler, num_nodes: torch.Tensor, context: Optional[torch.Tensor] = None,
                    num_timesteps: Optional[int] = None, group=None, gather: bool = True):
-    """Each rank samples its LPT shard with `sampler` (a GCDMSampler); returns (out_full or out_local, my_mols)."""
+    """Each rank samples its LPT shard with `sampler` (a GCDMSampler); returns (out_full or out_local, my_mols).
+
+    The per-rank noise streams are decorrelated here (see decorrelate_rank_rng).  A rank whose shard is empty (more
+    ranks than molecules) skips the chain and contributes a zero-row block, so the final collective still matches."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    decorrelate_rank_rng(rank)
     sizes = [int(v) for v in num_nodes.tolist()]
     mine = lpt_shards(sizes, world)[rank]
-    idx = torch.tensor(mine, dtype=torch.long)
-    local_nodes = num_nodes.cpu()[idx]
-    local_ctx = context.cpu()[idx] if context is not None else None
-    out, _, _ = sampler.sample(local_nodes, local_ctx, num_timesteps)
+    if mine:
+        idx = torch.tensor(mine, dtype=torch.long)
+        local_nodes = num_nodes.cpu()[idx]
+        local_ctx = context.cpu()[idx] if context is not None else None
+        out, _, _ = sampler.sample(local_nodes, local_ctx, num_timesteps)
+    else:
+        cfg = sampler.cfg
+        out = torch.zeros((0, 3 + cfg.num_atom_types + int(cfg.include_charges)), device=sampler._device())
     if not gather:
         return out, mine
     return gather_results(out, mine, sizes, world, group), mine
+
+
+def shard_imbalance(num_nodes: Sequence[int], world_size: int) -> float:
+    """max over ranks of the LPT shard cost (sum n^2) divided by the mean: 1.0 = perfectly balanced."""
+    shards = lpt_shards(num_nodes, world_size)
+    loads = [sum(int(num_nodes[i]) ** 2 for i in s) for s in shards]
+    mean = sum(loads) / max(1, world_size)
+    return max(loads) / mean if mean > 0 else 1.0
 
 
 def allreduce_mean_(tensors: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20) -> int:

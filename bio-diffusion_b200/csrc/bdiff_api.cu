@@ -55,6 +55,13 @@ struct bdiff_handle {
   std::vector<LayerW> layers;
   EmbedW embed{};
   std::map<std::string, bool> seen;   // reference parameter name -> set?
+  // raw copies of the reference tensors + the slice table: all slices are repacked by ONE kernel in bdiff_prepare
+  DevBuf stage_buf, jobs_dev;
+  size_t stage_used = 0;
+  std::map<std::string, size_t> stage_off;      // parameter name -> offset (floats) of its raw copy
+  std::vector<PackJob> jobs;
+  int pack_blocks = 0;
+  bool pack_dirty = false, jobs_uploaded = false;
 
   // plan
   bool have_plan = false;
@@ -364,7 +371,7 @@ void bdiff_destroy(bdiff_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
-  h->plan_buf.release(); h->rc_buf.release(); h->layers_dev.release(); h->sched_buf.release(); h->items_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release();
+  h->plan_buf.release(); h->rc_buf.release(); h->layers_dev.release(); h->sched_buf.release(); h->items_buf.release(); h->work_buf.release(); h->eps_buf.release(); h->tu_buf.release(); h->tc_blob.release(); h->tc_node_blob.release(); h->stage_buf.release(); h->jobs_dev.release();
   delete h;
 }
 
@@ -381,18 +388,46 @@ int32_t bdiff_set_weight(bdiff_handle* h, void* stream, const char* name, const 
     return h->fail(BDIFF_EINVAL, "parameter '%s': expected shape [%lld,%lld], got [%lld,%lld]", name, (long long)rows,
                    (long long)cols, (long long)got_rows, (long long)got_cols);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  for (const PackOp& op : ops) {
-    launch_pack(st, const_cast<float*>(op.dst), op.dst_ld, data, (int)cols, op.col0, op.ncols, op.kpad, op.nout);
-    h->launches++;
+  // raw copy into the staging area (device-to-device, stream ordered); the repack of all slices is one kernel in bdiff_prepare
+  const size_t count = (size_t)rows * (size_t)cols;
+  cudaError_t e = h->stage_buf.p ? cudaSuccess : h->stage_buf.ensure((h->wfloats + 64 * h->seen.size()) * sizeof(float));
+  if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "weight staging: %s", cudaGetErrorString(e));
+  auto so = h->stage_off.find(name);
+  size_t off;
+  if (so == h->stage_off.end()) {
+    off = h->stage_used;
+    h->stage_used += (count + 63) / 64 * 64;
+    if (h->stage_used * sizeof(float) > h->stage_buf.bytes) return h->fail(BDIFF_ENOMEM, "weight staging overflow");
+    h->stage_off[name] = off;
+    const float* src = static_cast<const float*>(h->stage_buf.p) + off;
+    for (const PackOp& op : ops) {
+      PackJob j{const_cast<float*>(op.dst), src, op.dst_ld, (int)cols, op.col0, op.ncols, op.kpad, op.nout, h->pack_blocks};
+      h->pack_blocks += (op.kpad * op.nout + 255) / 256;
+      h->jobs.push_back(j);
+    }
+    h->jobs_uploaded = false;
+  } else {
+    off = so->second;
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "pack '%s': %s", name, cudaGetErrorString(e));
+  e = cudaMemcpyAsync(static_cast<float*>(h->stage_buf.p) + off, data, count * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "stage '%s': %s", name, cudaGetErrorString(e));
   it->second = true;
+  h->pack_dirty = true;
   h->tc_dirty = true;
   return BDIFF_OK;
 }
 
 static void tc_prepare(bdiff_handle* h, cudaStream_t st) {
+  if (h->pack_dirty) {
+    if (!h->jobs_uploaded && h->jobs_dev.ensure(h->jobs.size() * sizeof(PackJob)) == cudaSuccess) {
+      cudaMemcpyAsync(h->jobs_dev.p, h->jobs.data(), h->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st);
+      cudaStreamSynchronize(st);    // pageable source; once per slice-table change, never inside a graph capture
+      h->jobs_uploaded = true;
+    }
+    launch_pack_multi(st, static_cast<const PackJob*>(h->jobs_dev.p), (int)h->jobs.size(), h->pack_blocks);
+    h->launches++;
+    h->pack_dirty = false;
+  }
   if (h->cfg.mode != BDIFF_MODE_TENSOR || !h->tc_dirty) return;
   for (int l = 0; l < h->d.L; ++l) {
     launch_tc_pack(st, h->layers[l], h->d, static_cast<unsigned char*>(h->tc_blob.p) + (size_t)l * h->tc_layer_bytes);

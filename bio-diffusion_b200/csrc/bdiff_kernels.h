@@ -50,8 +50,14 @@ void launch_step(cudaStream_t st, const Plan& p, const Dims& d, int mode, const 
                  float* out);
 void launch_edge_index(cudaStream_t st, const Plan& p, long long* out);
 void launch_edge_rc(cudaStream_t st, const Plan& p, int4* out, long long n);
-void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
-                 int kpad, int nout);
+// one slice of a reference parameter tensor -> kernel layout (see k_pack_multi)
+struct PackJob {
+  float* dst;
+  const float* src;
+  int dst_ld, src_ld, col0, ncols, kpad, nout;
+  int block0;              // first block of this job in the multi-slice launch (256 threads per block)
+};
+void launch_pack_multi(cudaStream_t st, const PackJob* jobs_dev, int njobs, int total_blocks);
 
 // tensor mode: per-layer split-bf16 weight streams (bdiff_tc_pack.cu)
 bool tc_supported(int Ed, int Xd);

@@ -889,13 +889,21 @@ __global__ void k_edge_rc(Plan p, int4* __restrict__ out, long long n) {
   out[g] = v;
 }
 
-// dst[k*dst_ld + o] = k < ncols ? src[o*src_ld + col0 + k] : 0   (torch [out,in] weight -> K-major, padded)
-__global__ void k_pack(float* __restrict__ dst, int dst_ld, const float* __restrict__ src, int src_ld, int col0,
-                       int ncols, int kpad, int nout) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= kpad * nout) return;
-  const int k = idx / nout, o = idx - k * nout;
-  dst[(size_t)k * dst_ld + o] = k < ncols ? src[(size_t)o * src_ld + col0 + k] : 0.f;
+// dst[k*dst_ld + o] = k < ncols ? src[o*src_ld + col0 + k] : 0   (torch [out,in] weight -> K-major, padded), for a whole
+// table of slices in ONE launch (a reference checkpoint is 432 tensors / ~950 slices): block b works on the job whose
+// [block0, block0 + blocks) range contains it.
+__global__ void k_pack_multi(const PackJob* __restrict__ jobs, int njobs) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {                       // last job with block0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const int idx = ((int)blockIdx.x - j.block0) * blockDim.x + threadIdx.x;
+  if (idx >= j.kpad * j.nout) return;
+  const int k = idx / j.nout, o = idx - k * j.nout;
+  j.dst[(size_t)k * j.dst_ld + o] = k < j.ncols ? j.src[(size_t)o * j.src_ld + j.col0 + k] : 0.f;
 }
 
 // ============================================================================================ launchers
@@ -951,10 +959,8 @@ void launch_edge_index(cudaStream_t st, const Plan& p, long long* out) {
 void launch_edge_rc(cudaStream_t st, const Plan& p, int4* out, long long n) {
   if (n > 0) k_edge_rc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, out, n);
 }
-void launch_pack(cudaStream_t st, float* dst, int dst_ld, const float* src, int src_ld, int col0, int ncols,
-                 int kpad, int nout) {
-  const int total = kpad * nout;
-  k_pack<<<(total + 255) / 256, 256, 0, st>>>(dst, dst_ld, src, src_ld, col0, ncols, kpad, nout);
+void launch_pack_multi(cudaStream_t st, const PackJob* jobs_dev, int njobs, int total_blocks) {
+  if (njobs > 0 && total_blocks > 0) k_pack_multi<<<total_blocks, 256, 0, st>>>(jobs_dev, njobs);
 }
 
 }  // namespace bdiff

@@ -12,6 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 class FakeSampler:
     """Stands in for GCDMSampler: row j of molecule with n atoms is [n, j, 100 n + j]."""
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(num_atom_types=0, include_charges=False)      # output width 3
+
+    def _device(self):
+        return torch.device("cpu")
 
     def sample(self, num_nodes, context=None, num_timesteps=None):
         rows = []
@@ -94,3 +99,22 @@ def test_allreduce_mean_single_process_is_noop():
     from bdiff.distributed import allreduce_mean_
     t = [torch.ones(3)]
     assert allreduce_mean_(t) == 0 and torch.equal(t[0], torch.ones(3))
+
+
+def test_more_ranks_than_molecules_does_not_hang():
+    """a rank with an empty shard must still take part in the final gather."""
+    sizes = [6]
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(2, 29519, sizes, results), nprocs=2, join=True)
+    expect, _, _ = FakeSampler().sample(torch.tensor(sizes))
+    for rank in (0, 1):
+        assert torch.equal(results[rank][0], expect)
+    assert results[1][1] == []
+
+
+def test_shard_imbalance_metric():
+    sys.path.insert(0, os.path.join(ROOT, "bio-diffusion_b200"))
+    from bdiff.distributed import shard_imbalance
+    assert shard_imbalance([19] * 8, 4) == 1.0
+    assert shard_imbalance([181, 3, 3, 3], 2) > 1.9
