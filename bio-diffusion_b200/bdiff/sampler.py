@@ -31,7 +31,7 @@ class GCDMSampler:
         self._graph = None
         self._static = None
         self.kernel_launches = 0     # libbdiff kernels launched (or replayed from the graph) by sample()
-        self.last_moments = None     # [T, 4] per-step (mean_x, std_x, mean_h, std_h) of z when sample(record_moments=True)
+        self.last_moments = None     # [T, 4] per-step (mean|x|, max|x|, mean h, mean|h|) of z when sample(record_moments=True)
 
     # -------------------------------------------------------------------------------------------- helpers
     def _device(self) -> torch.device:
@@ -128,7 +128,7 @@ class GCDMSampler:
         def record():
             # diagnostics only (tests): moments of the latent after this step, written at row `step` on the device
             zx, zh = st["z"][:, :3], st["z"][:, 3:]
-            m = torch.stack((zx.mean(), zx.std(), zh.mean(), zh.std())).view(1, 4)
+            m = torch.stack((zx.abs().mean(), zx.abs().max(), zh.mean(), zh.abs().mean())).view(1, 4)
             moments.index_copy_(0, st["step"].long().view(1), m)
 
         graph_ok = self.use_cuda_graph and noise is None

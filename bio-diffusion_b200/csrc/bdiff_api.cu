@@ -268,7 +268,7 @@ cudaError_t ensure_work(bdiff_handle* h) {
   w.nan_flag = reinterpret_cast<int*>(b + o_flag);
   w.dbg = nullptr;
   if (getenv("BDIFF_TIMING")) {
-    e = h->dbg_buf.ensure(256 * 64 * sizeof(long long));
+    e = h->dbg_buf.ensure(2 * 256 * 64 * sizeof(long long));
     if (e != cudaSuccess) return e;
     w.dbg = static_cast<long long*>(h->dbg_buf.p);
   }
@@ -781,7 +781,7 @@ int32_t bdiff_debug_tap(bdiff_handle* h, void* stream, const char* which, float*
   else if (s == "x") { src = w.x; *rows = N; *cols = 3; }
   else if (s == "fbar") { src = w.fbar; *rows = N; *cols = 12; }
   else if (s == "chi_in") { src = w.chi_in; *rows = N; *cols = 6; }
-  else if (s == "dbg" && w.dbg) { src = reinterpret_cast<const float*>(w.dbg); *rows = 256; *cols = 128; }
+  else if (s == "dbg" && w.dbg) { src = reinterpret_cast<const float*>(w.dbg); *rows = 512; *cols = 128; }
   else return h->fail(BDIFF_EINVAL, "unknown tap '%s'", which);
   if (dst && *rows * *cols > 0) {
     cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)(*rows) * (*cols) * sizeof(float), cudaMemcpyDeviceToDevice,

@@ -10,7 +10,7 @@ constexpr int TMT = 128;                 // edges per tile
 // weight ring: TC_NSLOT slots of TC_SLOT bytes; a chunk is one slab plane (N rows x 32 B, N <= 320) or a group of
 // small planes, always a single contiguous TMA bulk copy
 constexpr int TC_SLOT = 320 * 32;        // 10 KiB
-constexpr int TC_NSLOT = 4;
+constexpr int TC_NSLOT = 5;
 // TMEM column map of an edge tile (512 columns allocated)
 constexpr int TM_S = 0, TM_U0 = 256, TM_U1 = 288, TM_MV = 320, TM_VD0 = 416;
 constexpr int TM_EX = 416, TM_EX_STRIDE = 40;     // pair-exchange scratch (over VD0, which is dead by then): 2 x 40 columns
@@ -52,8 +52,7 @@ struct alignas(16) SmallW {   // fp32 copies of the thread-local (vector channel
 };
 
 struct EdgeTail : TcBars {
-  float2 sR[64][32];       // rows 64..127 of the reduction buffer (rows 0..63 live in A block 8, free by then)
-  float2 wbuf[8][2][32];   // per 16-row window: [0] head piece (segment entered from the previous window), [1] tail / whole piece
+  float2 wbuf[2][8][2][32];   // [round parity][16-row window]: [0] head piece (segment entered from the previous window), [1] tail / whole piece
   SmallW sw;
   float sAttn[2][TMT];
   int sRow[TMT], sCol[TMT], sB[TMT], sNa[TMT];

@@ -90,7 +90,6 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
     // ============================================================ scheduler + TMA producer (one lane)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
     if (lane == 0) {
-      TcBars& T = B;
       uint32_t ci = 0;
       for (uint32_t k = 0;; ++k) {
         const uint32_t slot = k & 1;
@@ -128,21 +127,35 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
     if (lane == 0) {
       TcBars& T = B;
-      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false),
-                     i32n = umma_idesc_bf16(32, true);
+      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false), i160 = umma_idesc_bf16(160, false),
+                     i144 = umma_idesc_bf16(144, false);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0, pu = 0;
-      auto wait_a = [&]() { mbar_wait_backoff(&B.a_ready, pa); pa ^= 1; tc_fence_after(); };
+      long long wcyc = 0, acyc = 0;          // BDIFF_TIMING: cycles this lane spent waiting for weights / for operands
+      auto wait_a = [&]() {
+        const long long t0 = w.dbg ? clock64() : 0;
+        mbar_wait_backoff(&B.a_ready, pa); pa ^= 1; tc_fence_after();
+        if (w.dbg) acyc += clock64() - t0;
+      };
       auto wait_w = [&]() -> uint32_t {
         const uint32_t s = ci % TC_NSLOT;
-        mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
+        if (w.dbg) {
+          const long long t0 = clock64();
+          mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
+          wcyc += clock64() - t0;
+        } else {
+          mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
+        }
         tc_fence_after();
         return raddr + s * TC_SLOT;
       };
       auto done_w = [&]() { umma_commit(&B.empty[ci % TC_NSLOT]); ++ci; };
       auto commit_d = [&]() { umma_commit(&B.d_full); };
       // node-tile GEMMs over A blocks 0..3 (R5 layout: views at row 0 and row 32, four products per K step).
-      // N = 256 or 288 plane rows; the 32 rows behind the first 256 go to U: umode 1 accumulates, 2 starts fresh and negated
+      // N = 256, or 288 plane rows whose last 32 go to the gate accumulator U (columns 256..287, contiguous with S): umode 1
+      // accumulates +Wg h_new, umode 2 starts U = -Wg h_old (sign folded into the packed weights).  With gate rows every
+      // product is two N=144 MMAs over the 288 contiguous columns; only the very first product is split 256 | 32 because the
+      // accumulate flags of S and U differ there.
       auto ngemm = [&](int N, uint32_t dcol, bool fresh, int umode) {
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t a = xaddr + (ks >> 2) * R5_BLOCK + (ks & 3) * 32;
@@ -150,12 +163,20 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
           for (int pl = 0; pl < 2; ++pl) {                   // hi plane, lo plane
             const uint32_t wb = wait_w();
             const bool first = ks == 0 && pl == 0;
-            umma_bf16(tmem + dcol, v0, umma_desc_k16(wb, N * 16, 128), i256, fresh ? !first : true);
-            umma_bf16(tmem + dcol, v1, umma_desc_k16(wb, N * 16, 128), i256, true);
-            if (umode) {
-              const uint64_t bu = umma_desc_k16(wb + 256 * 16, N * 16, 128);
-              umma_bf16(tmem + NM_U, v0, bu, umode == 2 ? i32n : i32, umode == 2 ? !first : true);
-              umma_bf16(tmem + NM_U, v1, bu, umode == 2 ? i32n : i32, true);
+            if (!umode) {
+              umma_bf16(tmem + dcol, v0, umma_desc_k16(wb, N * 16, 128), i256, fresh ? !first : true);
+              umma_bf16(tmem + dcol, v1, umma_desc_k16(wb, N * 16, 128), i256, true);
+            } else {
+              const uint64_t b0 = umma_desc_k16(wb, 288 * 16, 128), b1 = umma_desc_k16(wb + 144 * 16, 288 * 16, 128);
+              if (first) {
+                umma_bf16(tmem + NM_S, v0, b0, i256, !fresh);
+                umma_bf16(tmem + NM_U, v0, umma_desc_k16(wb + 256 * 16, 288 * 16, 128), i32, umode == 1);
+              } else {
+                umma_bf16(tmem + NM_S, v0, b0, i144, true);
+                umma_bf16(tmem + NM_S + 144, v0, b1, i144, true);
+              }
+              umma_bf16(tmem + NM_S, v1, b0, i144, true);
+              umma_bf16(tmem + NM_S + 144, v1, b1, i144, true);
             }
             done_w();
           }
@@ -178,11 +199,17 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         mbar_wait_backoff(&B.item_full[slot], (k >> 1) & 1);
         const int type = B.item[slot][0], layer = B.item[slot][1], tile = B.item[slot][2];
         if (type < 0) break;
+        const long long tstart = w.dbg ? clock64() : 0;
+        wcyc = 0; acyc = 0;
         if (type == 0) {
 #include "edge_tile_mma.inc"
         } else {
           const int last = layer == q.L - 1;
 #include "node_r4_tile_mma.inc"
+        }
+        if (w.dbg && k >= 2 && k < 4) {     // items 2, 3 of this CTA: {item code, total cycles, weight-wait, operand-wait}
+          long long* o = w.dbg + 256 * 64 + 148 * 64 + (size_t)blockIdx.x * 8 + (k - 2) * 4;
+          o[0] = (type << 30) | (layer << 24) | tile; o[1] = clock64() - tstart; o[2] = wcyc; o[3] = acyc;
         }
         mbar_wait_backoff(&B.tile_done, k & 1);
         __threadfence();
@@ -197,8 +224,14 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_COMPUTE));
     uint32_t pd = 0, pw = 0;
     int cur_type = -1, cur_layer = -1;
-    auto wait_d = [&]() { mbar_wait(&B.d_full, pd); pd ^= 1; tc_fence_after(); };
-    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&B.a_ready); };
+    // BDIFF_TIMING: phase stamps (clock64) of the first edge / node item with k >= 2 of every CTA: [128 + 0..31] edge,
+    // [128 + 32..63] node — one stamp before and after every accumulator wait, one after every operand publication
+    int es = 0;
+    long long* stamp = nullptr;
+    auto PH = [&]() { if (stamp && tid == 0 && es < 32) stamp[es] = clock64(); ++es; };
+    auto wait_d = [&]() { PH(); mbar_wait(&B.d_full, pd); pd ^= 1; tc_fence_after(); PH(); };
+    auto publish = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&B.a_ready); PH(); };
+    bool stamped[2] = {false, false};
     const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
     for (uint32_t k = 0;; ++k) {
@@ -280,6 +313,10 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
       named_bar_sync(3, TC_EPI);
       __threadfence();
       if (tid == 0 && w.dbg && k < 16) w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 2] = clock64();
+      es = 0;
+      stamp = nullptr;
+      if (w.dbg && k >= 2 && !stamped[type]) { stamp = w.dbg + 256 * 64 + (size_t)blockIdx.x * 64 + type * 32; stamped[type] = true; }
+      PH();
       if (type == 0) {
         EdgeTail& T = *reinterpret_cast<EdgeTail*>(tail);
         const int half = tid >> 7, r = tid & 127;
@@ -296,6 +333,7 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
       // ---- completion: every compute thread arrives (release) on tile_done after its last global write; the MMA
       //      lane — idle at this point — acquires it, makes the writes visible gpu-wide and raises the flag, so the
       //      ~1 us fence is off the compute warps' critical path
+      PH();
       if (tid == 0 && w.dbg && k < 16) w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 3] = clock64();
       mbar_arrive(&B.tile_done);
       mbar_arrive(&B.item_empty[slot]);

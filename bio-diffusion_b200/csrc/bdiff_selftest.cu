@@ -68,7 +68,78 @@ __global__ void __launch_bounds__(320, 1) k_umma_selftest_split(const float* __r
     for (int s = 0; s < ST_STEPS * 2; ++s) bulk_g2s(Wb + (size_t)s * ST_SLAB, wimg + (size_t)s * ST_SLAB, ST_SLAB, &bars[0]);
   }
   __syncthreads();
-  if (tid == 288) {
+  if (tid == 288 && variant >= 16) {
+    // ---- timing mode (tools/mma_timing.py): cycles of MMA streams of different shapes issued by one thread, A hi/lo blocks
+    // and the resident weight planes as operands (values irrelevant).  C[0] = cycles, C[1] = number of MMAs.
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t xa = smem_u32(X), wb0 = smem_u32(Wb);
+    const uint64_t adh = umma_desc_sw128(xa), adl = umma_desc_sw128(xa + 2 * X_BLOCK);
+    auto bdesc = [&](int ks, int pl, int row0) { return umma_desc_k16(wb0 + (uint32_t)((ks & 7) * 2 + pl) * ST_SLAB + row0 * 16, ST_N * 16, 128); };
+    auto adesc = [&](int ks, bool lo) { return (lo ? adl : adh) + (uint64_t)((((ks >> 2) & 1) * X_BLOCK + (ks & 3) * 32) >> 4); };
+    int n = 0;
+    const long long t0 = clock64();
+    if (variant >= 16 && variant <= 19) {
+      const int N = variant == 16 ? 256 : variant == 17 ? 32 : variant == 18 ? 64 : 160;
+      const uint32_t id = umma_idesc_bf16(N, false);
+      for (int ks = 0; ks < 32; ++ks)
+        for (int pr = 0; pr < 3; ++pr) { umma_bf16(tmem, adesc(ks, pr == 1), bdesc(ks, pr == 2, 0), id, true); ++n; }
+    } else if (variant == 20) {          // round-1/2a pattern: (256 | 32 | 32) x 3 products
+      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false), i32n = umma_idesc_bf16(32, true);
+      for (int ks = 0; ks < 16; ++ks)
+        for (int pr = 0; pr < 3; ++pr) {
+          const uint64_t ad = adesc(ks, pr == 1);
+          umma_bf16(tmem, ad, bdesc(ks, pr == 2, 0), i256, true);
+          umma_bf16(tmem + 256, ad, bdesc(ks, pr == 2, 256), i32, true);
+          umma_bf16(tmem + 288, ad, bdesc(ks, pr == 2, 288), i32n, true);
+          n += 3;
+        }
+    } else if (variant == 21) {          // (256 | 64) x 3
+      const uint32_t i256 = umma_idesc_bf16(256, false), i64 = umma_idesc_bf16(64, false);
+      for (int ks = 0; ks < 16; ++ks)
+        for (int pr = 0; pr < 3; ++pr) {
+          const uint64_t ad = adesc(ks, pr == 1);
+          umma_bf16(tmem, ad, bdesc(ks, pr == 2, 0), i256, true);
+          umma_bf16(tmem + 256, ad, bdesc(ks, pr == 2, 256), i64, true);
+          n += 2;
+        }
+    } else if (variant == 22) {          // (160 | 160) x 3
+      const uint32_t i160 = umma_idesc_bf16(160, false);
+      for (int ks = 0; ks < 16; ++ks)
+        for (int pr = 0; pr < 3; ++pr) {
+          const uint64_t ad = adesc(ks, pr == 1);
+          umma_bf16(tmem, ad, bdesc(ks, pr == 2, 0), i160, true);
+          umma_bf16(tmem + 160, ad, bdesc(ks, pr == 2, 160), i160, true);
+          n += 2;
+        }
+    } else if (variant >= 24 && variant <= 26) {   // (160 | 160) x 3 with the megakernel's per-plane bookkeeping
+      // 24: per plane one (already satisfied) full-barrier wait + fence and one commit;  25: waits per plane, ONE commit per
+      // K step;  26: commits per plane, no waits
+      const uint32_t i160 = umma_idesc_bf16(160, false);
+      if (tid == 288) { mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); mbar_fence_init(); }
+      for (int ks = 0; ks < 16; ++ks)
+        for (int pl = 0; pl < 2; ++pl) {
+          if (variant != 26) { mbar_wait(&bars[0], 0); tc_fence_after(); }
+          for (int pr = 0; pr < (pl == 0 ? 2 : 1); ++pr) {
+            const uint64_t ad = adesc(ks, pl == 0 && pr == 1);
+            umma_bf16(tmem, ad, bdesc(ks, pl, 0), i160, true);
+            umma_bf16(tmem + 160, ad, bdesc(ks, pl, 160), i160, true);
+            n += 2;
+          }
+          if (variant != 25 || pl == 1) umma_commit(&bars[2 + (pl & 1)]);
+        }
+    } else if (variant == 23) {          // 4 products of N=256 (node tile) x 16
+      const uint32_t i256 = umma_idesc_bf16(256, false);
+      for (int ks = 0; ks < 16; ++ks)
+        for (int pr = 0; pr < 4; ++pr) { umma_bf16(tmem, adesc(ks, pr & 1), bdesc(ks, pr >> 1, 0), i256, true); ++n; }
+    }
+    const long long t1 = clock64();
+    umma_commit(&bars[1]);
+    mbar_wait(&bars[1], 0);
+    const long long t2 = clock64();
+    C[0] = (float)(t2 - t0); C[1] = (float)n; C[2] = (float)(t1 - t0);
+  }
+  if (tid == 288 && variant < 16) {
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false), i32n = umma_idesc_bf16(32, true);
@@ -99,7 +170,7 @@ __global__ void __launch_bounds__(320, 1) k_umma_selftest_split(const float* __r
     }
     umma_commit(&bars[1]);
   }
-  if (tid < 256) {
+  if (tid < 256 && variant < 16) {
     mbar_wait(&bars[1], 0);
     tc_fence_after();
     const int half = tid >> 7, r = tid & 127;

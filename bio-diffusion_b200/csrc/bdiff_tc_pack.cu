@@ -8,7 +8,7 @@ size_t tc_blob_bytes(int Ed, int Xd) { return tc_edge_stream_bytes(Ed, Xd); }
 size_t tc_node_blob_bytes() { return tc_node_stream_bytes(0); }      // the last layer's stream is shorter
 
 // Edge pass:  G0: K0S steps x N=256 (W0e, zero-padded to K0S*16 rows)
-//             for k = 1..3:  16 steps x N=320 ([W_k[:, :256] | Wg_{k-1} | Wg_k]),  2 steps x N=256 (W_k rows 256..287)
+//             for k = 1..3:  16 steps x N=320 ([W_k[:, :256] | gate rows -> U0 | gate rows -> U1], see below),  2 steps x N=256 (W_k rows 256..287)
 //             G4: 16 steps x N=32 (Wg_3)
 // one thread per (plane row, k in [0,16)); writes the hi and the lo plane element
 __global__ void k_pack_edge_slabs(LayerW lw, Dims d, unsigned char* __restrict__ blob) {
@@ -37,9 +37,15 @@ __global__ void k_pack_edge_slabs(LayerW lw, Dims d, unsigned char* __restrict__
       if (rr < 16 * 320) {
         const int step = (int)(rr / 320);
         n = (int)(rr % 320); N = 320; base += (size_t)step * 2 * 320 * 32; k = step * 16 + kk;
+        // rows 256..287 accumulate into gate columns U0, rows 288..319 into U1.  GCP kk = gi + 1 adds +Wg_{kk-1} m_{kk-1} to
+        // U[(kk-1) & 1] and starts U[kk & 1] = -Wg_kk m_{kk-1} (the sign is folded into the packed weights, so that
+        // [S | U0 | U1] is ONE contiguous 320-column accumulator range for the fused MMAs)
+        const float* wprev = gi == 0 ? lw.Wg0 : lw.Wgk[gi - 1];
+        const float* wthis = lw.Wgk[gi];
+        const bool odd = ((gi + 1) & 1) != 0;           // kk odd: U0 <- +prev, U1 <- -this;  kk even: U0 <- -this, U1 <- +prev
         if (n < 256) v = lw.Wk[gi][(size_t)k * 256 + n];
-        else if (n < 288) v = (gi == 0 ? lw.Wg0 : lw.Wgk[gi - 1])[(size_t)k * 32 + (n - 256)];
-        else v = lw.Wgk[gi][(size_t)k * 32 + (n - 288)];
+        else if (n < 288) v = odd ? wprev[(size_t)k * 32 + (n - 256)] : -wthis[(size_t)k * 32 + (n - 256)];
+        else v = odd ? -wthis[(size_t)k * 32 + (n - 288)] : wprev[(size_t)k * 32 + (n - 288)];
       } else {
         rr -= 16 * 320;
         const int step = (int)(rr / 256);
@@ -84,7 +90,7 @@ __global__ void k_pack_node_slabs(LayerW lw, LayerW wn, EmbedW ew, Dims d, int l
     return false;
   };
   if (seg(16, 256)) v = lw.W1[(size_t)k * 256 + n];
-  else if (seg(16, 288)) v = n < 256 ? lw.W1[(size_t)(256 + k) * 256 + n] : lw.Wgf[(size_t)k * 32 + (n - 256)];
+  else if (seg(16, 288)) v = n < 256 ? lw.W1[(size_t)(256 + k) * 256 + n] : -lw.Wgf[(size_t)k * 32 + (n - 256)];   // U = -Wg h_old
   else if (seg(2, 256)) v = 512 + k < kKFF ? lw.W1[(size_t)(512 + k) * 256 + n] : 0.f;
   else if (seg(16, 256)) v = lw.W2[(size_t)k * 256 + n];
   else if (seg(16, 288)) v = n < 256 ? lw.Wp[(size_t)k * 256 + n] : lw.Wgf[(size_t)k * 32 + (n - 256)];

@@ -84,8 +84,12 @@ def test_forward_drop_in_contract():
     assert relerr(out.cpu(), fx["net_out"]) <= 5e-5
     # second call with the same Batch tensors reuses the plan
     key = net._plan_key
-    net(b, xh, fx["t"].cuda())
+    with torch.no_grad():
+        net(b, xh, fx["t"].cuda())
     assert net._plan_key == key
+    # under autograd with trainable parameters the module refuses loudly instead of returning a detached output
+    with pytest.raises(NotImplementedError):
+        net(b, xh, fx["t"].cuda())
 
 
 def test_forward_is_deterministic_and_batch_composable():
