@@ -62,3 +62,46 @@ def check_molecular_stability_batch(positions: torch.Tensor, atom_types: torch.T
     if rc != 0:
         raise _lib.BdiffError(f"bdiff_check_stability failed with code {rc}")
     return stable.bool(), nr_stable, nn.to(torch.int32).to(dev), nr_bonds
+
+
+def bond_orders_batch(positions: torch.Tensor, atom_types: torch.Tensor, num_nodes: torch.Tensor, dataset_info: dict,
+                      margins: Tuple[float, float, float] = (10.0, 5.0, 3.0)):
+    """The (X, A, E) graph `make_mol_edm` builds before handing it to RDKit (rdkit_functions.py:276-321), for a whole batch:
+    returns `bonds` int64 [M, 4] with rows (molecule, i, j, bond type) for every pair i > j with a bond, in the order the
+    reference's `torch.nonzero(A)` loop adds them to the RWMol, and the dense per-molecule int8 matrices E (packed, with
+    their offsets).  limit_bonds_to_one = ("GEOM" in dataset_info["name"]) as in the reference."""
+    if positions.device.type != "cuda":
+        raise _lib.BdiffError("bond_orders_batch runs on CUDA tensors only (no CPU fallback)")
+    lib = _lib.load()
+    dev = positions.device
+    dec = list(dataset_info["atom_decoder"])
+    a = len(dec)
+    tabs = [torch.as_tensor(np.asarray(dataset_info[k], dtype=np.float32)).reshape(a, a).contiguous().to(dev)
+            for k in ("bonds1", "bonds2", "bonds3")]
+    x = positions.detach().to(torch.float32).contiguous()
+    t = atom_types.detach().to(torch.int32).contiguous()
+    nn = num_nodes.detach().to(torch.int64).cpu()
+    n = int(x.shape[0])
+    if x.shape != (n, 3) or t.shape != (n,) or int(nn.sum()) != n or (nn < 0).any():
+        raise ValueError("positions [N,3], atom_types [N] and num_nodes (summing to N) expected")
+    b = int(nn.numel())
+    off = torch.zeros(b + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(nn, 0).to(torch.int32)
+    poff = torch.zeros(b + 1, dtype=torch.int64)
+    poff[1:] = torch.cumsum(nn * nn, 0)
+    e = torch.zeros(max(int(poff[-1]), 1), dtype=torch.int8, device=dev)
+    off_d, poff_d = off.to(dev), poff.to(dev)
+    limit = "GEOM" in str(dataset_info.get("name", ""))
+    rc = lib.bdiff_bond_orders(
+        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+        C.c_void_p(off_d.data_ptr()), C.c_void_p(poff_d.data_ptr()), C.c_int32(b), C.c_int32(a),
+        C.c_void_p(tabs[0].data_ptr()), C.c_void_p(tabs[1].data_ptr()), C.c_void_p(tabs[2].data_ptr()),
+        C.c_float(margins[0]), C.c_float(margins[1]), C.c_float(margins[2]), C.c_int32(int(limit)), C.c_void_p(e.data_ptr()))
+    if rc != 0:
+        raise _lib.BdiffError(f"bdiff_bond_orders failed with code {rc}")
+    flat = torch.nonzero(e[: int(poff[-1])]).reshape(-1)                     # ascending = (molecule, i, j) row-major
+    mol = torch.searchsorted(poff_d[1:], flat, right=True)
+    loc = flat - poff_d[mol]
+    nk = nn.to(dev)[mol]
+    bonds = torch.stack((mol, loc // nk, loc % nk, e[flat].to(torch.int64)), dim=1)
+    return bonds, e, poff_d

@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         } else {
           mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
         }
-        tc_fence_after();
+        // no tcgen05.fence here: the plane was written by the async proxy (TMA) and the mbarrier's acquire orders it before
+        // the MMAs this thread issues next; the fence is only needed after thread-written operands (wait_a)
         return raddr + s * TC_SLOT;
       };
       auto done_w = [&]() { umma_commit(&B.empty[ci % TC_NSLOT]); ++ci; };

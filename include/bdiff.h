@@ -198,6 +198,16 @@ BDIFF_API int32_t bdiff_check_stability(void* stream, const float* x, const int3
                                         const uint32_t* allowed_mask, int32_t limit_bonds_to_one, int32_t* nr_bonds,
                                         int32_t* nr_stable, int32_t* mol_stable);
 
+/* Bond-order matrix of `make_mol_edm` (src/datamodules/components/edm/rdkit_functions.py:276-321 with
+ * get_bond_order_batch, edm/__init__.py:61-88): for molecule k, bond_order[pair_off[k] + i*n + j] = bond type (0 none, 1, 2, 3)
+ * of the pair (i, j) for i > j and 0 otherwise (E = tril(E_full, -1): the directed graph the reference adds to the RWMol),
+ * with limit_bonds_to_one = ("GEOM" in dataset_info["name"]).  pair_off int64[B] = exclusive prefix sum of n_k^2.  Same
+ * tables / margins as bdiff_check_stability; all pointers are device pointers. */
+BDIFF_API int32_t bdiff_bond_orders(void* stream, const float* x, const int32_t* atom_types, const int32_t* mol_off,
+                                    const int64_t* pair_off, int32_t num_mols, int32_t num_types, const float* bonds1,
+                                    const float* bonds2, const float* bonds3, float margin1, float margin2, float margin3,
+                                    int32_t limit_bonds_to_one, int8_t* bond_order);
+
 /* Replaces: the warn-and-zero NaN guard of gcpnet.py:1214-1216 as an observable.  *count_host <- number of denoiser
  * forwards (since the last reset / re-plan of the workspace) in which a NaN position appeared and `vel` was zeroed.
  * Synchronises `stream`.  bench.py reports it for every timed chain. */

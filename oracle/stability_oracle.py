@@ -53,3 +53,23 @@ def check_stability_batch(x, atom_types, mol_off, bonds, margins, mask, limit_bo
         nr_stable[k] = int(sum(ok))
         mol_stable[k] = int(nr_stable[k] == b - a)
     return nb, nr_stable, mol_stable
+
+
+def bond_order_matrix(x, atom_types, bonds, margins, limit_bonds_to_one=False):
+    """E of `make_mol_edm` (rdkit_functions.py:287-296) for ONE molecule: tril(get_bond_order_batch(type_i, type_j, dist), -1)
+    as an int [n, n] array (atoms1, atoms2 = cartesian_prod(atom_types, atom_types).T -> (type_i, type_j) at i*n + j)."""
+    p = np.asarray(x, dtype=np.float32)
+    tt = np.asarray(atom_types, dtype=np.int64)
+    b1, b2, b3 = (np.asarray(b, dtype=np.float32) for b in bonds)
+    m1, m2, m3 = (np.float32(m) for m in margins)
+    d = p[:, None, :] - p[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    dist = np.float32(100.0) * np.sqrt(d2)
+    idx = (tt[:, None], tt[None, :])
+    order = np.zeros(dist.shape, dtype=np.int64)
+    order[dist < b1[idx] + m1] = 1
+    order[dist < b2[idx] + m2] = 2
+    order[dist < b3[idx] + m3] = 3
+    if limit_bonds_to_one:
+        order[order > 1] = 1
+    return np.tril(order, -1)

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_shim  # noqa: E402
 
 ref_shim.install()
-from src.datamodules.components.edm import check_molecular_stability, get_bond_length_arrays  # noqa: E402
+from src.datamodules.components.edm import check_molecular_stability, get_bond_length_arrays, get_bond_order_batch  # noqa: E402
 import src.datamodules.components.edm.constants as K  # noqa: E402
 from src.datamodules.components.edm.datasets_config import QM9_WITH_H, GEOM_WITH_H  # noqa: E402
 
@@ -47,16 +47,25 @@ def case(info, sizes, seed, spacing, extra=False):
     b = get_bond_length_arrays(enc)
     di = dict(info)
     di["bonds1"], di["bonds2"], di["bonds3"] = b
-    xs, ts, outs = [], [], []
+    xs, ts, outs, es = [], [], [], []
+    limit = "GEOM" in info["name"]
     mols = [molecule(rng, n, len(dec), spacing) for n in sizes] + (handmade(enc) if extra else [])
     sizes = [len(t) for _, t in mols]
     for p, t in mols:
         st, ns, nn = check_molecular_stability(torch.from_numpy(p), torch.from_numpy(np.asarray(t, dtype=np.int64)), di)
         xs.append(p); ts.append(np.asarray(t, dtype=np.int64)); outs.append((bool(st), int(ns), int(nn)))
+        # the (A, E) graph make_mol_edm hands to RDKit (rdkit_functions.py:287-296; RDKit itself is not installed here):
+        # the reference's own get_bond_order_batch on cartesian_prod(atom_types, atom_types), then tril(-1)
+        pt, tt = torch.from_numpy(p), torch.from_numpy(np.asarray(t, dtype=np.int64))
+        n = len(tt)
+        dists = torch.cdist(pt.unsqueeze(0), pt.unsqueeze(0), p=2).squeeze(0).view(-1)
+        a1, a2 = torch.cartesian_prod(tt, tt).T if n > 1 else (tt.repeat(1), tt.repeat(1))
+        e_full = get_bond_order_batch(a1, a2, dists, di, limit_bonds_to_one=limit).view(n, n)
+        es.append(torch.tril(e_full, diagonal=-1).to(torch.int8))
     return dict(atom_decoder=dec, bonds=[np.asarray(v, dtype=np.float32) for v in b],
                 margins=(K.margin1, K.margin2, K.margin3), allowed_bonds={k: K.allowed_bonds[k] for k in dec},
                 sizes=list(sizes), x=torch.from_numpy(np.concatenate(xs)), atom_types=torch.from_numpy(np.concatenate(ts)),
-                ref=outs)
+                ref=outs, bond_E=es, limit_bonds_to_one=limit)
 
 
 fx = {"qm9": case(QM9_WITH_H, [19, 5, 23, 1, 12, 29, 2, 17], 3, 1.15, extra=True),

@@ -45,3 +45,21 @@ def test_batched_stability_large_random_batch_vs_oracle():
     assert np.array_equal(nr_bonds.cpu().numpy(), nb)
     assert np.array_equal(nr_stable.cpu().numpy(), ns) and np.array_equal(stable.cpu().numpy().astype(np.int32), ms)
     assert nb.max() > 0
+
+
+@pytest.mark.parametrize("name", ["qm9", "geom"])
+def test_bond_order_matrix_matches_reference_graph(name):
+    """bdiff_bond_orders vs the (A, E) graph of the reference's make_mol_edm (stored fixture): same bonds, same order."""
+    from bdiff.stability import bond_orders_batch
+    fx = torch.load(os.path.join(GOLDEN, "stability.pt"), weights_only=False)[name]
+    info = {"atom_decoder": fx["atom_decoder"], "bonds1": fx["bonds"][0], "bonds2": fx["bonds"][1], "bonds3": fx["bonds"][2],
+            "name": "GEOM" if fx["limit_bonds_to_one"] else "QM9"}
+    bonds, e, poff = bond_orders_batch(fx["x"].cuda(), fx["atom_types"].cuda(), torch.tensor(fx["sizes"]), info, fx["margins"])
+    rows = []
+    for k, e_ref in enumerate(fx["bond_E"]):
+        n = fx["sizes"][k]
+        got = e[int(poff[k]): int(poff[k]) + n * n].reshape(n, n).cpu()
+        assert torch.equal(got, e_ref), k
+        nz = torch.nonzero(e_ref)                       # the reference's `all_bonds` loop order
+        rows += [(k, int(i), int(j), int(e_ref[i, j])) for i, j in nz.tolist()]
+    assert bonds.cpu().tolist() == [list(r) for r in rows]
