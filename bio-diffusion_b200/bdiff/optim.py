@@ -87,6 +87,9 @@ class GCDMTrainTail:
             C.byref(self.hyper))
         if rc != 0:
             raise _lib.BdiffError(f"bdiff_optimizer_step failed with code {rc}")
+        # the kernels wrote the parameters through raw pointers: bump their version counters so that everything keyed on
+        # (data_ptr, _version) — GCPNetDynamicsB200.sync_weights, autograd's saved-tensor checks — sees the update
+        torch.autograd.graph.increment_version(self.params)
         self.kernel_launches += 3
 
     def ema_parameters(self):

@@ -77,3 +77,24 @@ def test_full_denoiser_parameter_set_one_step():
         ref.step()
     for p, q in zip(net.parameters(), ref_params):
         assert torch.allclose(p, q, rtol=2e-6, atol=1e-8)
+
+
+def test_step_invalidates_the_denoisers_packed_weights():
+    """forward -> optimiser step -> forward must see the new parameters (version counters are bumped)."""
+    import bdiff
+    import gcpnet_oracle as O
+    net = bdiff.GCPNetDynamicsB200(config=bdiff.DenoiserConfig.named("geom"), mode="parity")
+    net.load_state_dict(O.random_state_dict(O.config_named("geom"), 1), strict=True)
+    net.cuda()
+    bi = torch.repeat_interleave(torch.arange(2), torch.tensor([7, 5])).cuda()
+    mask = torch.ones(12, dtype=torch.bool, device="cuda")
+    g = torch.Generator().manual_seed(0)
+    xh = torch.randn((12, 19), generator=g).cuda()
+    t = torch.full((12, 1), 0.4, device="cuda")
+    out0 = net.denoise(bi, mask, xh, t).clone()
+    opt = bdiff.GCDMTrainTail(list(net.parameters()))
+    for p in net.parameters():
+        p.grad.copy_(torch.randn(p.shape, generator=g).to(p.device))
+    opt.step()
+    out1 = net.denoise(bi, mask, xh, t)
+    assert not torch.equal(out0, out1), "the denoiser kept its old packed weights after an optimiser step"

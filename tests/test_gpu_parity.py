@@ -277,3 +277,18 @@ def test_optimize_chain_matches_reference_golden(name):
     assert torch.equal(out[:, 3:3 + a].cpu(), fx["out"][:, 3:3 + a])
     relx = (out[:, :3].cpu() - fx["out"][:, :3]).abs().max().item() / fx["out"][:, :3].abs().max().item()
     assert relx < 1e-4, relx
+
+
+def test_sample_sharded_on_one_gpu_equals_sample():
+    """bdiff.distributed.sample_sharded (the N>1 entry point: LPT shards + one gather) with a world of one rank returns what
+    GCDMSampler.sample returns for the same molecules and seed."""
+    import bdiff
+    from bdiff.distributed import sample_sharded
+    net, ocfg, sd = make_net("geom", 2)
+    sizes = torch.tensor([12, 30, 7, 44, 19])
+    s = bdiff.GCDMSampler(net)
+    torch.manual_seed(5)
+    ref, _, _ = s.sample(sizes, num_timesteps=4)
+    torch.manual_seed(5)
+    out, mine = sample_sharded(s, sizes, num_timesteps=4)
+    assert mine == list(range(5)) and torch.equal(out, ref)
