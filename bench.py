@@ -407,6 +407,40 @@ def run_ours(args):
                       "note": "same workload with BDIFF_MODE_PARITY_FP32 (every MAC an fp32 FFMA; 1e-6 from the reference)"}
         log(f"parity-mode chain done: {psecs:.2f} s")
 
+    # ---- "un-fused GPU" denominator: the reference's algorithm as un-fused PyTorch ops (the oracle port;
+    #      the reference modules themselves need PyG/torch_scatter and do not travel to this box) on THIS GPU, same batch
+    gpu_unfused = None
+    if world == 1 and not strong and not args.no_cpu_baseline:
+        try:
+            sd_dev = {k: v.to(dev) for k, v in sd.items()}
+            ei_dev = O.fully_connected_edge_index(bi.cpu(), mask.cpu()).to(dev)     # built once: generous to the baseline
+            orig_ei = O.fully_connected_edge_index
+            O.fully_connected_edge_index = lambda *_a, **_k: ei_dev
+            try:
+                with torch.device(dev), torch.no_grad():
+                    ref_out = O.denoiser_forward(sd_dev, ocfg, bi, mask, xh, tt, cnode)       # warm-up (+ agreement check)
+                    torch.cuda.synchronize()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    nf = 5
+                    ev0.record()
+                    for _ in range(nf):
+                        O.denoiser_forward(sd_dev, ocfg, bi, mask, xh, tt, cnode)
+                    ev1.record()
+                    torch.cuda.synchronize()
+            finally:
+                O.fully_connected_edge_index = orig_ei
+            ms_fwd = ev0.elapsed_time(ev1) / nf
+            ours = net.denoise(bi, mask, xh, tt, cnode, len(mine))
+            gpu_unfused = {"value": total_mols / (ms_fwd / 1000.0 * (T + 1)), "unit": "molecules/s", "ms_per_forward": ms_fwd,
+                           "kind": "port", "forwards_sampled": nf,
+                           "max_abs_diff_vs_ours": float((ours - ref_out).abs().max().item()),
+                           "note": "oracle port of the reference's PyG/torch_scatter algorithm run as un-fused PyTorch CUDA ops "
+                                   "on the same B200 and batch (edge index precomputed); denoiser forwards only, scaled to "
+                                   "the T+1 forwards of a sample"}
+            log(f"un-fused GPU port: {ms_fwd:.1f} ms/forward")
+        except Exception as ex:      # a baseline leg must never take the measurement down
+            gpu_unfused = {"unavailable": f"{type(ex).__name__}: {ex}"}
+
     imb = shard_imbalance(sizes_all.tolist(), world) if strong else 1.0
     line = {
         "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
@@ -442,6 +476,8 @@ def run_ours(args):
         line["shard_cost_imbalance"] = imb
     if parity_leg is not None:
         line["parity_fp32"] = parity_leg
+    if gpu_unfused is not None:
+        line["gpu_unfused_baseline"] = gpu_unfused
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_arm(args, reps=1)[0]
     if rank == 0:

@@ -53,6 +53,9 @@ PROTOTYPES = {
                               [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bdiff_bond_orders": (C.c_int32, [C.c_void_p] * 5 + [C.c_int32, C.c_int32] + [C.c_void_p] * 3 + [C.c_float] * 3 +
                           [C.c_int32, C.c_void_p]),
+    "bdiff_collate_count": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "bdiff_collate_packed": (C.c_int32, [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 4),
+    "bdiff_prepare_context": (C.c_int32, [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "bdiff_optimizer_chunk": (C.c_int32, []),
     "bdiff_optimizer_step": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),

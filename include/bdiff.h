@@ -208,6 +208,25 @@ BDIFF_API int32_t bdiff_bond_orders(void* stream, const float* x, const int32_t*
                                     const float* bonds2, const float* bonds3, float margin1, float margin2, float margin3,
                                     int32_t limit_bonds_to_one, int8_t* bond_order);
 
+/* ---- packed training collation ---------------------------------------------------------------------
+ * Replaces: ProcessedDataset._featurize_as_graph + PyG collation (datamodules/components/edm_dataset.py:187-216: molecules
+ * padded to `pad` atoms, mask = charges > 0) and prepare_context (datamodules/components/edm/utils.py:333-382).  The dataset
+ * stays on the device in padded form (positions f32[M,pad,3], charges i32[M,pad], one_hot u8[M,pad,A]); a batch = molecule
+ * ids idx i64[B].  bdiff_collate_count: counts[k] = present atoms of molecule idx[k].  bdiff_collate_packed: with
+ * mol_off i32[B+1] = exclusive prefix sum of the counts, writes the present atoms of the selected molecules in order:
+ * x f32[N,3], one_hot f32[N,A], charges f32[N] and batch_index i64[N] — the reference batch restricted to mask == True.
+ * bdiff_prepare_context: context[n,c] = (props[c][idx[batch_index[n]]] - mean[c]) / mad[c] for per-molecule properties
+ * props f32[C,M] (the reference's global-property branch; the node mask is all ones in a packed batch). */
+BDIFF_API int32_t bdiff_collate_count(void* stream, const int32_t* charges, const int64_t* idx, int32_t num_mols, int32_t pad,
+                                      int32_t* counts);
+BDIFF_API int32_t bdiff_collate_packed(void* stream, const float* positions, const int32_t* charges, const uint8_t* one_hot,
+                                       const int64_t* idx, const int32_t* mol_off, int32_t num_mols, int32_t pad,
+                                       int32_t num_types, float* x, float* one_hot_out, float* charges_out,
+                                       int64_t* batch_index);
+BDIFF_API int32_t bdiff_prepare_context(void* stream, const float* props, const int64_t* idx, const int64_t* batch_index,
+                                        const float* mean, const float* mad, int64_t dataset_size, int64_t num_nodes,
+                                        int32_t num_props, float* context);
+
 /* Replaces: the warn-and-zero NaN guard of gcpnet.py:1214-1216 as an observable.  *count_host <- number of denoiser
  * forwards (since the last reset / re-plan of the workspace) in which a NaN position appeared and `vel` was zeroed.
  * Synchronises `stream`.  bench.py reports it for every timed chain. */

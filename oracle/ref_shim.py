@@ -48,6 +48,12 @@ def _scatter(src, index, dim=0, out=None, dim_size=None, reduce="sum"):
     raise NotImplementedError(reduce)
 
 
+def _unbatch(src, batch, dim=0):
+    """torch_geometric.utils.unbatch (PyG 2.2.0): split `src` along `dim` by the (sorted) batch vector."""
+    sizes = torch.bincount(batch).tolist()
+    return src.split(sizes, dim)
+
+
 class _Batch:
     """Attribute bag standing in for torch_geometric.data.Batch on the sampling path."""
 
@@ -156,8 +162,9 @@ def install():
     tg.data = tgd
     sm["torch_geometric"] = tg
     sm["torch_geometric.data"] = tgd
-    for sub in ("loader", "utils", "nn", "transforms"):
+    for sub in ("loader", "nn", "transforms"):
         sm[f"torch_geometric.{sub}"] = MagicMock()
+    sm["torch_geometric.utils"] = _module("torch_geometric.utils", unbatch=_unbatch)
 
     sm["omegaconf"] = _module("omegaconf", DictConfig=_DictConfig, OmegaConf=_OmegaConf,
                               open_dict=_open_dict, ListConfig=list)
