@@ -35,6 +35,7 @@ PROTOTYPES = {
     "bdiff_weights_missing": (C.c_int32, [C.c_void_p]),
     "bdiff_prepare": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "bdiff_selftest_split": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bdiff_selftest_pair": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bdiff_plan_topology": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_int64)]),
     "bdiff_edge_index": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -463,6 +463,18 @@ int32_t bdiff_selftest_split(void* stream, int32_t variant, const float* A, cons
   return e == cudaSuccess ? BDIFF_OK : BDIFF_ECUDA;
 }
 
+int32_t bdiff_selftest_pair(void* stream, const float* A, const float* W, float* C) {
+  if (!A || !W || !C) return BDIFF_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (selftest_pair_configure() != cudaSuccess) return BDIFF_ECUDA;
+  void* img = nullptr;
+  if (cudaMalloc(&img, selftest_pair_img_bytes()) != cudaSuccess) return BDIFF_ENOMEM;
+  launch_umma_selftest_pair(st, A, W, static_cast<unsigned char*>(img), C);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(img);
+  return e == cudaSuccess ? BDIFF_OK : BDIFF_ECUDA;
+}
+
 int32_t bdiff_weights_missing(const bdiff_handle* h) {
   if (!h) return BDIFF_EINVAL;
   int n = 0;

@@ -84,6 +84,9 @@ cudaError_t tc_layers_configure();
 void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerSched& q,
                       const Work& w, int num_sms);
 cudaError_t selftest_configure();
+cudaError_t selftest_pair_configure();
+size_t selftest_pair_img_bytes();
+void launch_umma_selftest_pair(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C);
 size_t selftest_img_bytes();
 void launch_umma_selftest_split(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C,
                                 int variant);

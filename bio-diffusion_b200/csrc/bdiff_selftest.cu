@@ -198,6 +198,115 @@ __global__ void __launch_bounds__(320, 1) k_umma_selftest_split(const float* __r
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+
+// -------------------------------------------------------------------------------------------- CTA-pair self test
+// C[256][320] = A[256][128] . W[320][128]^T with cta_group::2 MMAs: a cluster of two CTAs, each with its own 128 A rows
+// (hi / lo blocks) and its own TMEM, while every weight plane is split between the two shared memories: CTA c holds plane
+// rows [80 c, 80 c + 80) for the first N=160 MMA and [160 + 80 c, 240 + 80 c) for the second one (local rows 80..159).
+// The peer's TMA completion is relayed to the leader by a remote mbarrier arrive; the leader's commit is multicast to both
+// CTAs.  This is the machinery the next version of the layer megakernel needs to halve its shared-memory traffic.
+constexpr int SP_LOCAL = 160;                               // plane rows per CTA
+constexpr int SP_SLAB = SP_LOCAL * 32;                      // bytes of one local plane of one K step
+constexpr size_t SP_SMEM = 4 * (size_t)X_BLOCK + (size_t)ST_STEPS * 2 * SP_SLAB + 128 + 1024;
+
+__global__ void k_selftest_pack_pair(const float* __restrict__ W, unsigned char* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ST_N * ST_K) return;
+  const int n = idx / ST_K, k = idx - n * ST_K;
+  const int mma = n / 160, within = n % 160, cta = within / 80, local = mma * 80 + within % 80;
+  // image = [cta][K step][hi plane | lo plane] with planes of SP_LOCAL rows
+  slab_store(img + ((size_t)cta * ST_STEPS + (k >> 4)) * 2 * SP_SLAB, SP_LOCAL, local, k & 15, W[idx]);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+    k_umma_selftest_pair(const float* __restrict__ A, const unsigned char* __restrict__ wimg, float* __restrict__ C) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* X = smem;
+  unsigned char* Wb = smem + 4 * X_BLOCK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Wb + (size_t)ST_STEPS * 2 * SP_SLAB);   // [0] full (local), [1] peer full (leader), [2] done
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
+    mbar_fence_init();
+  }
+  cluster_sync_all();                                  // barriers of both CTAs initialised before any remote arrive
+  if (warp == 8) tmem_alloc2(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  if (tid < 128) {
+    for (int k8 = 0; k8 < ST_K / 8; ++k8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = A[((size_t)rank * 128 + tid) * ST_K + k8 * 8 + q];
+      x_store8_hl(X, 2, tid, k8 * 8, v);
+    }
+    fence_proxy_async();
+  }
+  if (tid == 256) {                                    // TMA lane: this CTA's half of every plane
+    mbar_expect_tx(&bars[0], ST_STEPS * 2 * SP_SLAB);
+    const unsigned char* src = wimg + (size_t)rank * ST_STEPS * 2 * SP_SLAB;
+    for (int s = 0; s < ST_STEPS * 2; ++s) bulk_g2s(Wb + (size_t)s * SP_SLAB, src + (size_t)s * SP_SLAB, SP_SLAB, &bars[0]);
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // both A tiles written and visible to the async proxy of the pair
+  if (tid == 288) {
+    mbar_wait(&bars[0], 0);                            // my half has landed
+    if (rank == 1) {
+      mbar_arrive_remote(mapa_u32(&bars[1], 0));       // relay to the leader
+    } else {
+      mbar_wait(&bars[1], 0);                          // the peer's half has landed
+      tc_fence_after();
+      const uint32_t i160 = umma_idesc_bf16_m256(160);
+      for (int ks = 0; ks < ST_STEPS; ++ks) {
+        const uint32_t bh = smem_u32(Wb) + (uint32_t)ks * 2 * SP_SLAB, bl = bh + SP_SLAB;
+        const int j = ks >> 2, s = ks & 3;
+        const uint64_t ah = umma_desc_sw128(smem_u32(X) + j * X_BLOCK + s * 32);
+        const uint64_t al = umma_desc_sw128(smem_u32(X) + (2 + j) * X_BLOCK + s * 32);
+        for (int pr = 0; pr < 3; ++pr) {
+          const uint64_t ad = pr == 1 ? al : ah;
+          const uint32_t wb = pr == 2 ? bl : bh;
+          const bool acc = (ks | pr) > 0;
+          umma_bf16_pair(tmem + 0, ad, umma_desc_k16(wb, SP_LOCAL * 16, 128), i160, acc);
+          umma_bf16_pair(tmem + 160, ad, umma_desc_k16(wb + 80 * 16, SP_LOCAL * 16, 128), i160, acc);
+        }
+      }
+      umma_commit_pair(&bars[2]);
+    }
+  }
+  if (tid < 256) {
+    mbar_wait(&bars[2], 0);
+    tc_fence_after();
+    const int half = tid >> 7, r = tid & 127;
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = half * 160; c0 < half * 160 + 160; c0 += 32) {
+      float v[32];
+      tmem_ld32(tl + c0, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) C[((size_t)rank * 128 + r) * 320 + c0 + i] = v[i];
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // nobody leaves while the pair's TMEM / barriers are in use
+  if (warp == 8) tmem_dealloc2(tmem, 512);
+}
+
+cudaError_t selftest_pair_configure() {
+  return cudaFuncSetAttribute(k_umma_selftest_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
+}
+void launch_umma_selftest_pair(cudaStream_t st, const float* A, const float* W, unsigned char* img_scratch, float* C) {
+  k_selftest_pack_pair<<<(ST_N * ST_K + 255) / 256, 256, 0, st>>>(W, img_scratch);
+  k_umma_selftest_pair<<<2, 320, SP_SMEM, st>>>(A, img_scratch, C);
+}
+size_t selftest_pair_img_bytes() { return (size_t)2 * ST_STEPS * 2 * SP_SLAB; }
+
 cudaError_t selftest_configure() {
   return cudaFuncSetAttribute(k_umma_selftest_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
 }

@@ -89,6 +89,12 @@ BDIFF_API int32_t bdiff_prepare(bdiff_handle* h, void* stream);
  * W fp32[320,128] (device pointers).  variant bit 0 swaps LBO/SBO (must then FAIL the comparison).  Synchronises. */
 BDIFF_API int32_t bdiff_selftest_split(void* stream, int32_t variant, const float* A, const float* W, float* C);
 
+/* Hardware self test of the CTA-pair (cta_group::2) machinery: a two-CTA cluster, TMEM allocated for the pair, every weight
+ * plane split between the two shared memories, the peer's TMA completion relayed by a remote mbarrier arrive, one commit
+ * multicast to both CTAs.  C[256,320] <- A W^T for A fp32[256,128], W fp32[320,128] (device pointers), split-bf16 operands.
+ * Synchronises. */
+BDIFF_API int32_t bdiff_selftest_pair(void* stream, const float* A, const float* W, float* C);
+
 /* Replaces: GCPNetDynamics.get_fully_connected_edge_index (gcpnet.py:1054-1066) — as an implicit plan.
  * batch_index int64[N] (sorted molecule ids, as every caller provides), mask uint8[N].  Builds the
  * per-molecule offsets the kernels enumerate edges from; *num_edges_host receives E = sum_k nact_k^2.
