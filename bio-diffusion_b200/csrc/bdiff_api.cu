@@ -549,7 +549,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
     node_dep[2 * u + 1] = e1 >= e0 ? (int)(e1 / 128) : -1;
   }
   // per node: edge tiles strictly inside its row (their sums go through Work::mid, see edge_tile_epilogue.inc)
-  const int Npad128 = round_up(N, 128);
+  const int Npad128 = round_up(N, 128) + 128;          // node buffers carry one spare 128-row block (ghost node tile of an odd pair)
   std::vector<int> node_mid((size_t)2 * Npad128, 0);
   for (int k = 0; k < B; ++k) {
     const long long na = act_off[k + 1] - act_off[k];
@@ -594,7 +594,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   p.edge_rc = nullptr;
   p.node_mid = reinterpret_cast<const int2*>(base + o_mid);
   {
-    const long long nrc = ntile128 * 128;
+    const long long nrc = (ntile128 + 1) * 128;       // + one ghost tile (row = -1): the second CTA of the last pair when the tile count is odd
     e = h->rc_buf.ensure((size_t)(nrc > 0 ? nrc : 1) * sizeof(int4));
     if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "plan edge records: %s", cudaGetErrorString(e));
     launch_edge_rc(st, p, static_cast<int4*>(h->rc_buf.p), nrc);
@@ -607,27 +607,39 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   h->sched.TE = (int)ntile128;
   h->sched.TN = ntile32;
   {
-    // Claim order of the layer megakernel.  Virtual time of edge (l, t) = l*TE + t; node (l, u) follows the last edge
-    // tile it reads by `lag` claims (about one wave: by then that tile has normally finished).  Every dependency must
-    // precede its consumer in the list (deadlock freedom), which bounds the lag: edge (l+1, t) reads node (l, u) for
-    // u <= edge_dep[t].y, whose time is l*TE + node_dep[u].y + lag  <  (l+1)*TE + t.
+    // Claim order of the layer megakernel, in PAIR items: a CTA pair works on tiles (2j, 2j+1) of one kind and layer (the
+    // second tile of the last pair is a ghost when the count is odd).  Virtual time of edge pair (l, j) = l*PE + j; node pair
+    // (l, v) follows the last edge pair it reads by `lag` claims (about one wave: by then that pair has normally finished).
+    // Every dependency must precede its consumer in the list (deadlock freedom), which bounds the lag: edge pair (l+1, j)
+    // reads node pairs <= ndep(j), whose time is l*PE + edep(ndep) + lag  <  (l+1)*PE + j.
     const int L = h->d.L, TE = (int)ntile128, TN = ntile32;
+    const int PE = (TE + 1) / 2, PN = (TN + 1) / 2;
     if (L > 63 || ntile128 >= (1 << 24) || ntile32 >= (1 << 24)) return h->fail(BDIFF_EINVAL, "problem too large for the tile scheduler");
-    long long lag = h->num_sms;
-    for (int t = 0; t < TE; ++t) {
-      const int uh = edge_dep[2 * t + 1];
-      const int th = uh < TN ? node_dep[2 * uh + 1] : -1;
-      if (th >= 0) lag = std::min<long long>(lag, (long long)TE - 1 - (th - t));
+    auto node_pair_last_edge_pair = [&](int v) {          // last edge pair a node pair depends on (-1: none)
+      int th = -1;
+      for (int u = 2 * v; u < std::min(TN, 2 * v + 2); ++u) th = std::max(th, node_dep[2 * u + 1]);
+      return th >= 0 ? th / 2 : -1;
+    };
+    auto edge_pair_last_node_pair = [&](int j) {
+      int uh = -1;
+      for (int t = 2 * j; t < std::min(TE, 2 * j + 2); ++t) uh = std::max(uh, edge_dep[2 * t + 1]);
+      return uh >= 0 ? uh / 2 : -1;
+    };
+    long long lag = std::max(1, h->num_sms / 2);
+    for (int j = 0; j < PE; ++j) {
+      const int vh = edge_pair_last_node_pair(j);
+      const int jh = (vh >= 0 && vh < PN) ? node_pair_last_edge_pair(vh) : -1;
+      if (jh >= 0) lag = std::min<long long>(lag, (long long)PE - 1 - (jh - j));
     }
     if (lag < 0) lag = 0;
     std::vector<std::pair<long long, int>> order;
-    order.reserve((size_t)L * (TE + TN));
+    order.reserve((size_t)L * (PE + PN));
     for (int l = 0; l < L; ++l) {
-      for (int t = 0; t < TE; ++t) order.emplace_back(2 * ((long long)l * TE + t), (0 << 30) | (l << 24) | t);
-      for (int u = 0; u < TN; ++u) {
-        const int th = node_dep[2 * u + 1];       // -1: no edges at all -> right at the start of the layer
-        const long long tau = (long long)l * TE + (th >= 0 ? th + lag : 0);
-        order.emplace_back(2 * tau + 1, (1 << 30) | (l << 24) | u);
+      for (int j = 0; j < PE; ++j) order.emplace_back(2 * ((long long)l * PE + j), (0 << 30) | (l << 24) | j);
+      for (int v = 0; v < PN; ++v) {
+        const int jh = node_pair_last_edge_pair(v);     // -1: no edges at all -> right at the start of the layer
+        const long long tau = (long long)l * PE + (jh >= 0 ? jh + lag : 0);
+        order.emplace_back(2 * tau + 1, (1 << 30) | (l << 24) | v);
       }
     }
     std::stable_sort(order.begin(), order.end(), [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a.first < b.first; });
@@ -637,6 +649,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
     if (e == cudaSuccess && !items.empty())
       e = cudaMemcpy(h->items_buf.p, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "scheduler work list: %s", cudaGetErrorString(e));
+    h->sched.nitems = (int)items.size();
     h->sched.items = static_cast<const int*>(h->items_buf.p);
   }
   {
@@ -647,7 +660,7 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
     h->sched.err = h->sched.sched + nsched;
     cudaMemset(h->sched.err, 0, sizeof(int));
   }
-  h->Npad = round_up(N, 128);
+  h->Npad = round_up(N, 128) + 128;
   h->Epad = (E + 127) / 128 * 128 + 128;
   e = ensure_work(h);
   if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "workspace: %s", cudaGetErrorString(e));

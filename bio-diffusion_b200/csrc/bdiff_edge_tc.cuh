@@ -9,7 +9,7 @@ namespace bdiff {
 constexpr int TMT = 128;                 // edges per tile
 // weight ring: TC_NSLOT slots of TC_SLOT bytes; a chunk is one slab plane (N rows x 32 B, N <= 320) or a group of
 // small planes, always a single contiguous TMA bulk copy
-constexpr int TC_SLOT = 320 * 32;        // 10 KiB
+constexpr int TC_SLOT = 2 * 160 * 32;    // 10 KiB: this CTA's half of the widest K step (hi plane + lo plane)
 constexpr int TC_NSLOT = 5;
 // TMEM column map of an edge tile (512 columns allocated)
 constexpr int TM_S = 0, TM_U0 = 256, TM_U1 = 288, TM_MV = 320, TM_VD0 = 416;
@@ -25,9 +25,9 @@ __host__ __device__ inline size_t tc_edge_stream_bytes(int Ed, int Xd) {
 
 // mbarriers / bookkeeping of the megakernel; first member (base class) of both tile tails
 struct TcBars {
-  uint64_t full[TC_NSLOT], empty[TC_NSLOT], a_ready, d_full, wbar, u_free;
-  uint64_t item_full[2], item_empty[2], tile_done;
-  int item[2][4];          // work items {type, layer, tile, -}
+  uint64_t full[TC_NSLOT], empty[TC_NSLOT], pfull[TC_NSLOT], a_ready, d_full, wbar, u_free;
+  uint64_t item_full[2], item_empty[2], peer_empty[2], tile_done;
+  alignas(16) int item[2][4];   // work items {type, layer, tile of THIS CTA, -}; the leader writes the peer's copy (16-byte st.shared::cluster)
   uint32_t tmem_ptr;
   uint32_t pad_;
 };

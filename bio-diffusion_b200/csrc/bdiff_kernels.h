@@ -74,11 +74,12 @@ struct LayerSched {
   const unsigned char* node_blob;
   size_t node_blob_stride;
   int L, TE, TN;                   // layers, 128-edge tiles, 32-node tiles
+  int nitems;                      // pair items in the work list: L * (ceil(TE/2) + ceil(TN/2))
   int* sched;                      // [0] queue head, [1] unused, [2 + l*(TE+TN) + i] completion flags; zeroed per forward
   int* err;                        // sticky error word (dependency wait timed out); cleared when the plan is built / reported
   const int2* edge_dep;            // [TE] inclusive range of 32-node tiles whose previous-layer output an edge tile reads
   const int2* node_dep;            // [TN] inclusive range of edge tiles whose messages a node tile reads
-  const int* items;                // [L*(TE+TN)] work list in claim order: type<<30 | layer<<24 | tile (see bdiff_plan_topology)
+  const int* items;                // [nitems] work list in claim order: type<<30 | layer<<24 | PAIR index: a CTA pair works on tiles 2j, 2j+1 (see bdiff_plan_topology)
 };
 cudaError_t tc_layers_configure();
 void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerSched& q,

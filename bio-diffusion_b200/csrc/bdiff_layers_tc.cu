@@ -42,6 +42,17 @@ union LayersTail {
 constexpr size_t LAYERS_SMEM_BYTES = XE_BLOCKS * (size_t)X_BLOCK + TC_NSLOT * (size_t)TC_SLOT + sizeof(LayersTail) + 1024;
 static_assert(LAYERS_SMEM_BYTES <= 232448, "shared memory budget of the layer megakernel");
 
+// The grid is a set of CTA PAIRS (thread-block clusters of 2, cta_group::2): a pair works on two consecutive tiles of the same
+// kind and layer at a time (CTA rank r on tile 2j + r), ONE thread of the leader CTA (rank 0) issues every MMA for both SMs
+// (M = 256: each CTA's own A tile and TMEM), and every weight plane is SPLIT between the two shared memories, so each SM
+// streams, stores and reads only half of the weights: 2.3 GB of L2->SM weight traffic per QM9 forward instead of 4.6 GB and
+// 49 KB instead of 74 KB of shared-memory traffic per K step.  Cross-CTA protocol: events are forwarded to the leader by single
+// RELAXED remote mbarrier arrives — the peer's operand publications / U releases by a relay lane (warp 10), its TMA
+// completions by one relay lane per ring slot (warp 9); the leader's commits are multicast to both CTAs (ring slots, d_full);
+// work items are claimed by the leader's scheduler lane and handed to the peer through distributed shared memory.
+// (Measured: same speed as the single-CTA version — 60.9 vs 61.2 molecules/s — the MMA phases are bound by the
+// instruction mix (N=64 / N=32 MMAs at ~50 cycles, per-K-step bookkeeping of the issuing lane), not by operand bandwidth.)
+//
 // 12 warps: 0-7 compute (two warpgroups), 8 scheduler + TMA producer, 9 MMA issuer, 10-11 padding so that the
 // service warps form a complete third warpgroup for setmaxnreg.  The CTA is launched with 168 registers/thread
 // (384 threads -> a pool of 64512); the service warpgroup shrinks to 96 and the two compute warpgroups grow to 200
@@ -50,8 +61,28 @@ constexpr int LAYERS_THREADS = 384;
 constexpr int LAYERS_REG_COMPUTE = 200, LAYERS_REG_SERVICE = 96;
 static_assert(256 * LAYERS_REG_COMPUTE + 128 * LAYERS_REG_SERVICE <= 168 * LAYERS_THREADS, "setmaxnreg pool");
 
+// acquire at cluster scope: the item slot / remote arrivals come from the other CTA of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, int a, int b, int c, int d) {
+  asm volatile("st.shared::cluster.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 template <int ED, int XD>
-__global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d, EmbedW ew, LayerSched q, Work w) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LAYERS_THREADS, 1)
+    k_layers_tc(Plan p, Dims d, EmbedW ew, LayerSched q, Work w) {
   constexpr int HID0 = (64 + XD) / 4;
   constexpr int H2 = HID0 / 2;
   constexpr int K0RAW = ED + HID0 + 9;
@@ -67,24 +98,33 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int hid0 = d.hid0;
   const int per_layer = q.TE + q.TN;
-  const int total_items = q.L * per_layer;
+  const int total_items = q.nitems;                 // pair items
   int* const flags = q.sched + 2;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair
+  const bool leader = rank == 0;
 
   if (tid == 0) {
-    for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&B.full[i], 1); mbar_init(&B.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&B.item_full[i], 1); mbar_init(&B.item_empty[i], TC_EPI + 1); }
+    for (int i = 0; i < TC_NSLOT; ++i) { mbar_init(&B.full[i], 1); mbar_init(&B.empty[i], 1); mbar_init(&B.pfull[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&B.item_full[i], 1); mbar_init(&B.item_empty[i], leader ? TC_EPI + 1 : TC_EPI + 2); mbar_init(&B.peer_empty[i], 1);
+    }
     mbar_init(&B.tile_done, TC_EPI);
-    mbar_init(&B.a_ready, TC_EPI);
+    mbar_init(&B.a_ready, leader ? TC_EPI + 1 : TC_EPI);   // leader's: its own compute threads + ONE arrival relayed by the peer's MMA lane
     mbar_init(&B.d_full, 1);
     mbar_init(&B.wbar, 1);
-    mbar_init(&B.u_free, TC_EPI);
+    mbar_init(&B.u_free, leader ? TC_EPI + 1 : TC_EPI);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc(&B.tmem_ptr, 512);
+  cluster_sync_all();                               // the barriers of both CTAs exist before any remote arrive
+  if (warp == 8) tmem_alloc2(&B.tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = B.tmem_ptr;
+  // Cross-CTA events are forwarded by ONE relaxed remote arrive of the peer's MMA lane (an arrive.release.cluster costs the
+  // issuing thread ~800 cycles of fencing, and 256 of them per phase — or one per weight plane — made the first pair version
+  // slower than the single-CTA kernel).  The data itself never crosses SMs: every tensor core reads its own SM's shared memory.
+  const uint32_t a_ready_leader = mapa_u32(&B.a_ready, 0), u_free_leader = mapa_u32(&B.u_free, 0);
 
   if (warp == 8) {
     // ============================================================ scheduler + TMA producer (one lane)
@@ -94,17 +134,31 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
       for (uint32_t k = 0;; ++k) {
         const uint32_t slot = k & 1;
         mbar_wait_backoff(&B.item_empty[slot], ((k >> 1) & 1) ^ 1);
-        const int qi = atomicAdd(q.sched, 1);
         int type = -1, layer = 0, tile = 0;
-        if (qi < total_items) {
-          const int it = __ldg(q.items + qi);
-          type = (it >> 30) & 1; layer = (it >> 24) & 63; tile = it & 0xffffff;
+        if (leader) {
+          // the peer's copy of this item slot is free as well (its scheduler lane relays its item_empty)
+          mbar_wait_backoff(&B.peer_empty[slot], (k >> 1) & 1);
+          const int qi = atomicAdd(q.sched, 1);
+          int pair = 0;
+          if (qi < total_items) {
+            const int it = __ldg(q.items + qi);
+            type = (it >> 30) & 1; layer = (it >> 24) & 63; pair = it & 0xffffff;
+          }
+          B.item[slot][0] = type; B.item[slot][1] = layer; B.item[slot][2] = 2 * pair;
+          st_cluster_v4(mapa_u32(&B.item[slot][0], 1), type, layer, 2 * pair + 1, 0);
+          mbar_arrive(&B.item_full[slot]);
+          mbar_arrive_remote(mapa_u32(&B.item_full[slot], 1));      // release.cluster: the item words are visible to the peer
+          tile = 2 * pair;
+        } else {
+          mbar_arrive_remote_relaxed(mapa_u32(&B.peer_empty[slot], 0));
+          mbar_wait_cluster(&B.item_full[slot], (k >> 1) & 1);
+          type = B.item[slot][0]; layer = B.item[slot][1]; tile = B.item[slot][2];
         }
-        B.item[slot][0] = type; B.item[slot][1] = layer; B.item[slot][2] = tile;
-        mbar_arrive(&B.item_full[slot]);
+        (void)tile;
         if (type < 0) break;
-        const unsigned char* blob = type == 0 ? q.edge_blob + (size_t)layer * q.edge_blob_stride
-                                              : q.node_blob + (size_t)layer * q.node_blob_stride;
+        // this CTA's half of the layer's weight stream: [rank 0 stream | rank 1 stream]
+        const unsigned char* blob = type == 0 ? q.edge_blob + (size_t)layer * q.edge_blob_stride + rank * (q.edge_blob_stride / 2)
+                                              : q.node_blob + (size_t)layer * q.node_blob_stride + rank * (q.node_blob_stride / 2);
         size_t off = 0;
         auto push = [&](uint32_t bytes) {
           const uint32_t s = ci % TC_NSLOT;
@@ -122,82 +176,103 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         }
       }
     }
+  } else if (warp == 9 && !leader) {
+    // ============ peer: its weight planes are consumed by MMAs the LEADER issues, so their TMA completions (local full barriers)
+    // are forwarded to the leader's pfull barriers.  A remote arrive keeps the issuing thread busy for ~600 cycles: one lane per
+    // ring slot shares the work.  Lane 0 also publishes the completion flag of the peer's tile.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
+    if (lane < TC_NSLOT) {
+      const uint32_t pfull0 = mapa_u32(&B.pfull[0], 0);
+      uint32_t ci = 0;
+      for (uint32_t k = 0;; ++k) {
+        const uint32_t slot = k & 1;
+        mbar_wait_cluster(&B.item_full[slot], (k >> 1) & 1);
+        const int type = B.item[slot][0], layer = B.item[slot][1], tile = B.item[slot][2];
+        if (type < 0) break;
+        const uint32_t nch = type == 0 ? K0S + 3 * 18 + 4 : (layer == q.L - 1 ? 73u : 100u);      // chunks per tile (producer includes)
+        // lane = ring slot: a lane sees the phases of ITS slot's barrier strictly in order (waiting for a phase two uses ahead
+        // would alias with the parity of the current one)
+        for (uint32_t cc = ci + ((lane + TC_NSLOT - ci % TC_NSLOT) % TC_NSLOT); cc < ci + nch; cc += TC_NSLOT) {
+          mbar_wait_backoff(&B.full[lane], (cc / TC_NSLOT) & 1);
+          mbar_arrive_remote_relaxed(pfull0 + lane * 8);
+        }
+        ci += nch;
+        if (lane == 0) {
+          mbar_wait_backoff(&B.tile_done, k & 1);
+          __threadfence();
+          if (tile < (type == 0 ? q.TE : q.TN))
+            st_release_gpu(flags + (size_t)layer * per_layer + (type == 0 ? tile : q.TE + tile), 1);
+          mbar_arrive(&B.item_empty[slot]);
+        }
+      }
+    }
   } else if (warp == 9) {
-    // ======================================================================= MMA issuer (one lane)
+    // =============================== leader: MMA lane, issues every pair MMA (cta_group::2) for both CTAs
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
     if (lane == 0) {
       TcBars& T = B;
-      const uint32_t i256 = umma_idesc_bf16(256, false), i32 = umma_idesc_bf16(32, false), i160 = umma_idesc_bf16(160, false),
-                     i144 = umma_idesc_bf16(144, false);
+      const uint32_t i256 = umma_idesc_bf16_m256(256), i64 = umma_idesc_bf16_m256(64), i32 = umma_idesc_bf16_m256(32);
       const uint32_t xaddr = smem_u32(X), raddr = smem_u32(ring);
       uint32_t ci = 0, pa = 0, pu = 0;
       long long wcyc = 0, acyc = 0;          // BDIFF_TIMING: cycles this lane spent waiting for weights / for operands
       auto wait_a = [&]() {
+        if (!leader) return;                                   // the peer's operands are announced by its relay lane (warp 10)
         const long long t0 = w.dbg ? clock64() : 0;
-        mbar_wait_backoff(&B.a_ready, pa); pa ^= 1; tc_fence_after();
+        mbar_wait_backoff(&B.a_ready, pa); pa ^= 1;
+        tc_fence_after();
         if (w.dbg) acyc += clock64() - t0;
       };
+      // leader: both halves of the plane have landed (mine: full, the peer's: pfull, relayed);  peer: relay, no MMAs
       auto wait_w = [&]() -> uint32_t {
-        const uint32_t s = ci % TC_NSLOT;
-        if (w.dbg) {
-          const long long t0 = clock64();
-          mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
-          wcyc += clock64() - t0;
-        } else {
-          mbar_wait_backoff(&B.full[s], (ci / TC_NSLOT) & 1);
-        }
-        // no tcgen05.fence here: the plane was written by the async proxy (TMA) and the mbarrier's acquire orders it before
-        // the MMAs this thread issues next; the fence is only needed after thread-written operands (wait_a)
+        const uint32_t s = ci % TC_NSLOT, par = (ci / TC_NSLOT) & 1;
+        const long long t0 = w.dbg ? clock64() : 0;
+        mbar_wait_backoff(&B.full[s], par);
+        mbar_wait_backoff(&B.pfull[s], par);
+        if (w.dbg) wcyc += clock64() - t0;
         return raddr + s * TC_SLOT;
       };
-      auto done_w = [&]() { umma_commit(&B.empty[ci % TC_NSLOT]); ++ci; };
-      auto commit_d = [&]() { umma_commit(&B.d_full); };
-      // node-tile GEMMs over A blocks 0..3 (R5 layout: views at row 0 and row 32, four products per K step).
-      // N = 256, or 288 plane rows whose last 32 go to the gate accumulator U (columns 256..287, contiguous with S): umode 1
-      // accumulates +Wg h_new, umode 2 starts U = -Wg h_old (sign folded into the packed weights).  With gate rows every
-      // product is two N=144 MMAs over the 288 contiguous columns; only the very first product is split 256 | 32 because the
-      // accumulate flags of S and U differ there.
-      auto ngemm = [&](int N, uint32_t dcol, bool fresh, int umode) {
+      auto done_w = [&]() { if (leader) umma_commit_pair(&B.empty[ci % TC_NSLOT]); ++ci; };
+      auto commit_d = [&]() { if (leader) umma_commit_pair(&B.d_full); };
+      auto mma = [&](uint32_t dcol, uint64_t ad, uint64_t bd, uint32_t idesc, bool acc) { if (leader) umma_bf16_pair(tmem + dcol, ad, bd, idesc, acc); };
+      // node-tile GEMMs over A blocks 0..3 (R5 layout: views at row 0 and row 32, four products per K step).  Local plane =
+      // [128 rows of the S columns | 16 gate rows] (NL rows): S is one N=256 pair MMA, the gate accumulator U (columns 256..287)
+      // one N=32 pair MMA: umode 1 accumulates +Wg h_new, umode 2 starts U = -Wg h_old (sign folded into the packed weights).
+      auto ngemm = [&](int NL, uint32_t dcol, bool fresh, int umode) {
         for (int ks = 0; ks < 16; ++ks) {
           const uint32_t a = xaddr + (ks >> 2) * R5_BLOCK + (ks & 3) * 32;
           const uint64_t v0 = umma_desc_sw128(a), v1 = umma_desc_sw128(a + 4096);
-          for (int pl = 0; pl < 2; ++pl) {                   // hi plane, lo plane
-            const uint32_t wb = wait_w();
+          const uint32_t wb0 = wait_w();                      // one chunk = this K step's [hi plane | lo plane]
+          for (int pl = 0; pl < 2; ++pl) {
+            const uint32_t wb = wb0 + pl * NL * 32;
             const bool first = ks == 0 && pl == 0;
-            if (!umode) {
-              umma_bf16(tmem + dcol, v0, umma_desc_k16(wb, N * 16, 128), i256, fresh ? !first : true);
-              umma_bf16(tmem + dcol, v1, umma_desc_k16(wb, N * 16, 128), i256, true);
-            } else {
-              const uint64_t b0 = umma_desc_k16(wb, 288 * 16, 128), b1 = umma_desc_k16(wb + 144 * 16, 288 * 16, 128);
-              if (first) {
-                umma_bf16(tmem + NM_S, v0, b0, i256, !fresh);
-                umma_bf16(tmem + NM_U, v0, umma_desc_k16(wb + 256 * 16, 288 * 16, 128), i32, umode == 1);
-              } else {
-                umma_bf16(tmem + NM_S, v0, b0, i144, true);
-                umma_bf16(tmem + NM_S + 144, v0, b1, i144, true);
-              }
-              umma_bf16(tmem + NM_S, v1, b0, i144, true);
-              umma_bf16(tmem + NM_S + 144, v1, b1, i144, true);
+            const uint64_t bs = umma_desc_k16(wb, NL * 16, 128);
+            mma(dcol, v0, bs, i256, fresh ? !first : true);
+            mma(dcol, v1, bs, i256, true);
+            if (umode) {
+              const uint64_t bu = umma_desc_k16(wb + 128 * 16, NL * 16, 128);
+              mma(NM_U, v0, bu, i32, umode == 2 ? !first : true);
+              mma(NM_U, v1, bu, i32, true);
             }
-            done_w();
           }
+          done_w();
         }
       };
       auto nextra = [&]() {                                  // += [vn | q] (block 4, 32 columns) . W[:, 256:288]
         for (int ks = 0; ks < 2; ++ks) {
           const uint32_t a = xaddr + 4 * R5_BLOCK + ks * 32;
           const uint64_t v0 = umma_desc_sw128(a), v1 = umma_desc_sw128(a + 4096);
+          const uint32_t wb0 = wait_w();
           for (int pl = 0; pl < 2; ++pl) {
-            const uint32_t wb = wait_w();
-            umma_bf16(tmem + NM_S, v0, umma_desc_k16(wb, 256 * 16, 128), i256, true);
-            umma_bf16(tmem + NM_S, v1, umma_desc_k16(wb, 256 * 16, 128), i256, true);
-            done_w();
+            const uint32_t wb = wb0 + pl * 128 * 32;
+            mma(NM_S, v0, umma_desc_k16(wb, 128 * 16, 128), i256, true);
+            mma(NM_S, v1, umma_desc_k16(wb, 128 * 16, 128), i256, true);
           }
+          done_w();
         }
       };
       for (uint32_t k = 0;; ++k) {
         const uint32_t slot = k & 1;
-        mbar_wait_backoff(&B.item_full[slot], (k >> 1) & 1);
+        mbar_wait_cluster(&B.item_full[slot], (k >> 1) & 1);
         const int type = B.item[slot][0], layer = B.item[slot][1], tile = B.item[slot][2];
         if (type < 0) break;
         const long long tstart = w.dbg ? clock64() : 0;
@@ -214,12 +289,34 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
         }
         mbar_wait_backoff(&B.tile_done, k & 1);
         __threadfence();
-        st_release_gpu(flags + (size_t)layer * per_layer + (type == 0 ? tile : q.TE + tile), 1);
+        if (tile < (type == 0 ? q.TE : q.TN))       // a ghost tile (odd tile count) has no flag
+          st_release_gpu(flags + (size_t)layer * per_layer + (type == 0 ? tile : q.TE + tile), 1);
         mbar_arrive(&B.item_empty[slot]);
       }
     }
-  } else if (warp >= 10) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));     // padding warps of the service warpgroup
+  } else if (warp == 10) {
+    // ============ peer only: event relay lane.  It waits on the peer's LOCAL a_ready / u_free (the peer's 256 compute threads)
+    // and forwards each completion to the leader's barrier with one relaxed remote arrive.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));
+    if (lane == 0 && !leader) {
+      uint32_t pa = 0, pu = 0;
+      for (uint32_t k = 0;; ++k) {
+        const uint32_t slot = k & 1;
+        mbar_wait_cluster(&B.item_full[slot], (k >> 1) & 1);
+        const int type = B.item[slot][0], layer = B.item[slot][1];
+        if (type < 0) break;
+        const bool has_u = type == 1 && layer != q.L - 1;
+        const int nph = type == 0 ? 8 : 6;                      // operand publications per tile (edge: G0, 3 x (a, b), G4)
+        for (int ph = 0; ph < nph; ++ph) {
+          if (has_u && ph == 4) { mbar_wait_backoff(&B.u_free, pu); pu ^= 1; mbar_arrive_remote_relaxed(u_free_leader); }
+          mbar_wait_backoff(&B.a_ready, pa); pa ^= 1;
+          mbar_arrive_remote_relaxed(a_ready_leader);
+        }
+        mbar_arrive(&B.item_empty[slot]);
+      }
+    }
+  } else if (warp >= 11) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_SERVICE));     // padding warp of the service warpgroup
   } else {
     // ============================================================================ compute / epilogue warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(LAYERS_REG_COMPUTE));
@@ -237,9 +334,10 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
     auto sz = [](int n) { return (uint32_t)((n * 4 + 15) & ~15); };
     for (uint32_t k = 0;; ++k) {
       const uint32_t slot = k & 1;
-      mbar_wait(&B.item_full[slot], (k >> 1) & 1);
+      mbar_wait_cluster(&B.item_full[slot], (k >> 1) & 1);
       const int type = B.item[slot][0], layer = B.item[slot][1], tile = B.item[slot][2];
       if (type < 0) break;
+      const bool real = tile < (type == 0 ? q.TE : q.TN);      // odd tile counts: the last pair's second CTA runs a ghost tile
       if (tid == 0 && w.dbg && k < 16) {      // BDIFF_TIMING: {item code, t_fetch, t_start, t_end} for the first 16 items
         w.dbg[(size_t)blockIdx.x * 64 + 4 * k] = (type << 30) | (layer << 24) | tile;
         w.dbg[(size_t)blockIdx.x * 64 + 4 * k + 1] = clock64();
@@ -287,7 +385,7 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
       }
       // ---- dependencies: completion flags of the producer tiles (bounded spin), then a gpu-scope acquire in
       //      every thread before it reads activations written by other SMs
-      if (tid == 0) {
+      if (tid == 0 && real) {
         int lo = 0, hi = -1;
         const int* fbase = flags;
         if (type == 0) {
@@ -342,7 +440,8 @@ __global__ void __launch_bounds__(LAYERS_THREADS, 1) k_layers_tc(Plan p, Dims d,
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  cluster_sync_all();                               // nobody leaves while the pair's barriers / TMEM may still be addressed
+  if (warp == 8) tmem_dealloc2(tmem, 512);
 }
 
 bool tc_supported(int Ed, int Xd) { return (Ed == 64 && Xd == 16) || (Ed == 16 && Xd == 8); }
@@ -356,8 +455,8 @@ cudaError_t tc_layers_configure() {
 
 void launch_layers_tc(cudaStream_t st, const Plan& p, const Dims& d, const EmbedW& ew, const LayerSched& q,
                       const Work& w, int num_sms) {
-  const int items = q.L * (q.TE + q.TN);
-  const int grid = items < num_sms ? items : num_sms;
+  int grid = 2 * q.nitems < num_sms ? 2 * q.nitems : num_sms;
+  grid &= ~1;                                       // CTA pairs
   if (d.Ed == 64) k_layers_tc<64, 16><<<grid, LAYERS_THREADS, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
   else k_layers_tc<16, 8><<<grid, LAYERS_THREADS, LAYERS_SMEM_BYTES, st>>>(p, d, ew, q, w);
 }

@@ -97,6 +97,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t cta) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// (a plain cp.async.bulk whose mbarrier lives in the OTHER CTA of the pair never completes — tried; only the tensor-map TMA
+// forms have the cta_group::2 variant that signals the leader's barrier — hence the relay lanes of the layer megakernel)
+// same without the release: for pure event forwarding (nothing this thread wrote has to become visible with the arrival)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {   // one full warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
                : "memory");
