@@ -4,21 +4,21 @@
 // rounds (19 % of the SM time idle in the last one at the BASELINE batch) and the node pass has work for only 76
 // SMs — and pays ~18 launch / prologue / pipeline-ramp gaps.  Nothing in the network couples molecules inside a
 // layer (gcpnet.py:676-737, 893-930: messages, aggregation and node updates are per molecule), so layer l+1 of
-// a molecule only needs layer l of the same molecule.  This kernel therefore runs the per-tile bodies of
-// k_edge_message_tc and k_node_update_r4 (the very same code, textually included) from a global work list
-//     for l in 0..L-1:  edge tiles (l, 0..TE-1) in order, node tile (l, u) inserted ~one wave of claims after the last
-//                       edge tile it depends on (so its wait is short and the CTA that claims it does not idle)
+// a molecule only needs layer l of the same molecule.  This kernel therefore runs the edge-tile and node-tile bodies
+// (edge_tile_*.inc, node_r4_tile_*.inc) from a global work list of tile PAIRS (see below)
+//     for l in 0..L-1:  edge pairs (l, 0..PE-1) in order, node pair (l, v) inserted ~one wave of claims after the last
+//                       edge pair it depends on (so its wait is short and the CTA pair that claims it does not idle)
 // claimed with one atomicAdd per item, with per-tile completion flags as dependencies:
 //     edge (l, t)  waits for node (l-1, u) of every 32-node tile u that intersects the molecules of edge tile t;
 //     node (l, u)  waits for edge (l, t) of every edge tile t that intersects the molecules of node tile u.
-// Every dependency has a smaller queue index and all CTAs are resident (grid <= #SMs, 1 CTA/SM), so the smallest
-// unfinished item can always run: no deadlock.  Spins are bounded (~1 s) and raise a sticky error word (bdiff_check) instead of hanging.
+// Every dependency has a smaller queue index and a pair only claims an item once it is running, so the smallest unfinished
+// item can always run: no deadlock.  A dependency wait beyond 2^32 cycles can only mean a broken schedule: it traps (sticky
+// launch failure + error word read by bdiff_check) instead of computing on stale data.
 // Flags are released with fence + st.release after a CTA barrier and acquired with ld.acquire + a gpu-scope fence
 // in every consumer thread (mutable activations are re-read from L2, not from a stale L1 line).
 //
-// Warp roles as in the per-pass kernels; the TMA-producer lane also claims the items (so the next tile's weights
-// stream while the current tile computes) and hands them to the MMA lane and the 8 compute warps through a
-// two-slot mbarrier ring.
+// The TMA-producer lane also claims the items (so the next tile's weights stream while the current tile computes) and hands
+// them to the MMA lane and the 8 compute warps through a two-slot mbarrier ring.
 #include "bdiff_node_tc.cuh"
 
 namespace bdiff {
