@@ -38,7 +38,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="qm9", choices=["qm9", "qm9_cond", "geom", "geom_hist"])
+    ap.add_argument("--config", default="qm9", choices=["qm9", "qm9_cond", "geom", "geom_hist", "geom_train"],
+                    help="sampling workloads, or geom_train = BASELINE config 5 (training step, 64 molecules per GPU)")
+    ap.add_argument("--train-tf32", action="store_true", help="geom_train: TF32 tensor-core GEMMs instead of fp32")
     ap.add_argument("--batch", type=int, default=None, help="molecules per GPU (default 128; geom 64; geom_hist: 512 in TOTAL)")
     ap.add_argument("--atoms", type=int, default=None, help="atoms per molecule (default 19 qm9 / 44 geom)")
     ap.add_argument("--timesteps", type=int, default=1000)
@@ -104,7 +106,7 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- workloads
 def model_config(args):
-    return "geom" if args.config == "geom_hist" else args.config
+    return "geom" if args.config in ("geom_hist", "geom_train") else args.config
 
 
 def workload_sizes(args, world):
@@ -486,6 +488,198 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE config 5: GEOM-Drugs denoiser training step — GCDMTrainLoss (training pass of the library: forward with tape),
+    loss.backward() (bdiff_train_backward), DDP-style gradient mean over the ranks (one NCCL all-reduce), adaptive clip +
+    AdamW(amsgrad) + EMA kernels.  `batch` (64) molecules per GPU with sizes from the GEOM histogram; a step takes a NEW batch
+    (new topology plan), like a data loader would deliver it."""
+    import torch.distributed as dist
+    import bdiff
+    from bdiff.datasets import GEOM_N_NODES, sample_num_nodes
+    from bdiff.distributed import allreduce_mean_
+    from bdiff.optim import GCDMTrainTail
+    import gcpnet_oracle as O   # seeded synthetic weights + the CPU baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dcfg = bdiff.DenoiserConfig.named("geom")
+    ocfg = O.config_named("geom")
+    sd = O.random_state_dict(ocfg, seed=7)
+    net = bdiff.GCPNetDynamicsB200(config=dcfg, mode="parity")
+    net.load_state_dict(sd, strict=True)
+    net.to(dev)
+    net.flatten_parameters()
+    net.set_train_precision(args.train_tf32)
+    opt = GCDMTrainTail(net.parameters())
+    tl = bdiff.GCDMTrainLoss(net, GEOM_N_NODES)
+    B = args.batch or 64
+    nb = 4                                                       # distinct host batches, cycled
+    A = dcfg.num_atom_types
+    batches, edges = [], []
+    for b in range(nb):
+        sizes = sample_num_nodes(GEOM_N_NODES, B, seed=1000 * (rank + 1) + b)
+        g = torch.Generator().manual_seed(17 * (rank + 1) + b)
+        bi = torch.repeat_interleave(torch.arange(B), sizes)
+        n = int(bi.shape[0])
+        x = torch.randn((n, 3), generator=g) * 2.0
+        x = x - (torch.zeros((B, 3)).index_add_(0, bi, x) / sizes[:, None].float())[bi]
+        one_hot = torch.nn.functional.one_hot(torch.randint(0, A, (n,), generator=g), A).float()
+        batches.append(tuple(v.pin_memory() for v in (bi, torch.ones(n, dtype=torch.bool), x, one_hot, torch.zeros((n, 0)))))
+        edges.append(int((sizes.long() ** 2).sum()))
+    dev_batches = [tuple(v.to(dev) for v in hb) for hb in batches]
+    loss_host = torch.zeros((), pin_memory=True)
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    counter = [0]
+    finite = [True]
+
+    def train_step(batch):
+        opt.zero_grad()
+        loss = tl(*batch, None)[0].mean()
+        loss.backward()
+        if world > 1:
+            allreduce_mean_(opt.grads)                           # DDP: mean of the gradients, one bucketed all-reduce
+        opt.step()
+        return loss.detach()
+
+    def step_resident():
+        loss = train_step(dev_batches[counter[0] % nb])
+        counter[0] += 1
+        return loss
+
+    def step_e2e():
+        hb = batches[counter[0] % nb]
+        counter[0] += 1
+        loss = train_step(tuple(v.to(dev, non_blocking=True) for v in hb))      # H2D of this step's batch (pinned)
+        loss_host.copy_(loss, non_blocking=True)                                # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        finite[0] = finite[0] and bool(torch.isfinite(loss_host))
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        barrier()
+        for _ in range(k):
+            flush_buf.fill_(1.0)
+            barrier()
+            ev0.record()
+            fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            total += ev0.elapsed_time(ev1)
+        barrier()
+        t = torch.tensor([total], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / 1000.0
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    l0, k0 = net.launch_count(), opt.kernel_launches
+    if rank == 0:
+        clocks.start()
+    counter[0] = 0
+    secs = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    launches = (net.launch_count() - l0) + (opt.kernel_launches - k0)
+    counter[0] = 0
+    secs_e2e = timed(step_e2e, args.steps)
+    fin = torch.tensor([int(finite[0])], device=dev)
+    if world > 1:
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+    if not bool(fin.item()):
+        raise SystemExit("bench.py: a timed training step produced a non-finite loss")
+
+    # phases of one step (events on the launch stream, batch 0, after the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    batch = dev_batches[0]
+    opt.zero_grad()
+    torch.cuda.synchronize()
+    ev[0].record()
+    loss = tl(*batch, None)[0].mean()
+    ev[1].record()
+    loss.backward()
+    ev[2].record()
+    if world > 1:
+        allreduce_mean_(opt.grads)
+    ev[3].record()
+    opt.step()
+    ev[4].record()
+    torch.cuda.synchronize()
+    phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("loss_forward", "backward", "allreduce", "optimizer"))}
+    # roofline: the step is GEMM-bound; algorithmic FLOPs = forward (793 kFLOP per edge and layer + 575 kFLOP per node and
+    # layer, SURVEY.md §8d) x 3 (forward, input gradients, weight gradients)
+    E0, n0 = edges[0], int(batch[0].shape[0])
+    flops = 3.0 * dcfg.num_layers * (E0 * 793224 + n0 * 575324)
+    t_fb = (phases["loss_forward"] + phases["backward"]) / 1000.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    mols = B * world * args.steps
+    line = {
+        "metric": "molecules/sec (GEOM-Drugs training step: forward + backward + gradient all-reduce + optimizer)",
+        "value": mols / secs, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1000 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32 GEMMs, f32 elsewhere" if args.train_tf32 else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"GEOM-Drugs denoiser training step, {B} molecules per GPU, sizes ~ dataset histogram, a new batch "
+                               f"(new topology plan) every step",
+                   "config_name": "geom_train", "edges_per_batch_rank0": edges, "weights": "random init (seed 7)",
+                   "objective": "GCDMTrainLoss = reference training-mode L2 objective (t ~ U{0..T}, one denoiser call)",
+                   "optimizer": "adaptive gradient-norm clip + AdamW(amsgrad) + EMA 0.9999 (bdiff_optimizer_step)",
+                   "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": f"dp{world}: one batch per rank, gradients averaged with one bucketed NCCL all-reduce per step"},
+        "e2e": {"value": mols / secs_e2e, "unit": "molecules/s", "ms_per_step": 1000 * secs_e2e / args.steps,
+                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in batches[0])), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches) * world,
+        "library_calls": "GEMMs of the training pass are cuBLAS SGEMM calls (not counted in gpu_launches)",
+        "losses_finite": True, "clocks": clk, "phase_ms_batch0": phases,
+        "roofline": {"bound": "tensor", "achieved": flops / t_fb / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": flops / t_fb / 1e12 / tensor_peak, "traffic": None,
+                     "kernel": "forward + backward of the training pass (cuBLAS SGEMMs + element kernels), batch 0",
+                     "algorithmic_flops": flops, "ms": 1000 * t_fb,
+                     "note": "fp32 SGEMM does not run on the tensor pipe: against the bf16 tensor peak this fraction is small "
+                             "by construction; it is reported so that the gap to a tcgen05 training pass is visible"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        # the same objective on the host: autograd through the oracle port, first `cpu_mols` molecules of batch 0
+        cpu_mols = 4
+        bi, mask, x, one_hot, charges = batches[0]
+        nn0 = int((bi < cpu_mols).sum())
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        torch.manual_seed(1)
+        t0 = time.perf_counter()
+        lc, _ = O.eval_nll(sdg, ocfg, bi[:nn0], mask[:nn0], x[:nn0], one_hot[:nn0], charges[:nn0], None, GEOM_N_NODES,
+                           lambda s_: torch.randn(s_), training=True)
+        lc.mean().backward()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": cpu_mols / dt, "unit": "molecules/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"one forward+backward (torch autograd through the oracle port) of the first {cpu_mols} "
+                                          f"molecules of batch 0 ({nn0} atoms), {dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def sampler_launches(sampler, net):
     return getattr(sampler, "kernel_launches", 0)
 
@@ -494,6 +688,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "geom_train":
+        run_train(args)
     else:
         run_ours(args)
 

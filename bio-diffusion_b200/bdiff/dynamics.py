@@ -8,6 +8,12 @@ with strict=True, state-dict prefix `ddpm.dynamics_network.`), same call contrac
 but every arithmetic step runs in libbdiff_sm100.so (hand-written sm_100a kernels).  To plug it into the
 reference, add it to the `dynamics_networks` dict of src/models/qm9_mol_gen_ddpm.py:101-105.
 There is no CPU / PyTorch fallback: tensors must live on a CUDA device and the library must be built.
+
+Under autograd (`torch.is_grad_enabled()` and trainable parameters — what the reference's training_step does,
+qm9_mol_gen_ddpm.py:340-362) `forward` runs the library's training pass instead of the sampler kernels:
+`bdiff_train_forward` keeps the tape, `loss.backward()` reaches `bdiff_train_backward` through a
+`torch.autograd.Function` and every parameter receives its gradient (no gradient flows to xh / t: in the GCDM objective
+they are data).
 """
 from __future__ import annotations
 
@@ -44,6 +50,28 @@ def _register(root: nn.Module, dotted: str, param: nn.Parameter) -> None:
     mod.register_parameter(parts[-1], param)
 
 
+class _DenoiseTrainFn(torch.autograd.Function):
+    """net_out = denoiser(params; xh, t, context) with the library's tape; backward = bdiff_train_backward."""
+
+    @staticmethod
+    def forward(ctx, net, batch_index, mask, xh, t, context, num_mols, *params):
+        out = net._train_forward(batch_index, mask, xh, t, context, num_mols)
+        ctx.net = net
+        ctx.tape_id = net._tape_id
+        ctx.needs = tuple(p.requires_grad for p in params)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_out):
+        net = ctx.net
+        if ctx.tape_id != net._tape_id:
+            raise RuntimeError("GCPNetDynamicsB200 keeps ONE training tape: a later forward under autograd replaced the "
+                               "one this backward needs (call backward() before the next training forward)")
+        grads = net._train_backward(d_out)
+        return (None,) * 7 + tuple(g if need else None for g, need in zip(grads, ctx.needs))
+
+
 class GCPNetDynamicsB200(nn.Module):
     def __init__(self, model_cfg=None, module_cfg=None, layer_cfg=None, diffusion_cfg=None, dataloader_cfg=None,
                  *, config: Optional[DenoiserConfig] = None, mode: str = "parity"):
@@ -63,6 +91,10 @@ class GCPNetDynamicsB200(nn.Module):
         self._plan_info = None       # (B, N, E)
         self._plan_epoch = 0         # bumped by every bdiff_plan_topology call (device buffers may have moved)
         self._keepalive = None
+        self._flat = None            # training: the parameters are views of this flat buffer (library layout)
+        self._grad_flat = None
+        self._layout = None          # name -> (offset, count)
+        self._tape_id = 0
 
     # ------------------------------------------------------------------------------------------ parameters
     def reset_parameters(self) -> None:
@@ -197,16 +229,105 @@ class GCPNetDynamicsB200(nn.Module):
             C.c_void_p(out.data_ptr())), "bdiff_denoise_forward")
         return out
 
+    def wants_grad(self) -> bool:
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def forward(self, batch: Any, xh: torch.Tensor, t: torch.Tensor, **kwargs: Any):
-        """Reference contract: gcpnet.py:1042-1052.  Reads batch.batch / batch.mask / batch.props_context."""
+        """Reference contract: gcpnet.py:1042-1052.  Reads batch.batch / batch.mask / batch.props_context.
+        Under autograd with trainable parameters the result carries a grad_fn (training pass), else sampler kernels."""
         if kwargs.get("xh_self_cond") is not None or kwargs.get("x_self_cond") is not None:
             raise NotImplementedError("self-conditioning is not supported (shipped configs have self_condition=false)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward through GCPNetDynamicsB200 is not implemented yet (inference path)")
         ctx = getattr(batch, "props_context", None)
         num_mols = getattr(batch, "num_graphs", None)
-        net_out = self.denoise(batch.batch, batch.mask, xh, t, ctx, num_mols if isinstance(num_mols, int) else None)
-        return batch, net_out
+        num_mols = num_mols if isinstance(num_mols, int) else None
+        fn = self.denoise_train if self.wants_grad() else self.denoise
+        return batch, fn(batch.batch, batch.mask, xh, t, ctx, num_mols)
+
+    # ------------------------------------------------------------------------------------------ training pass
+    def flatten_parameters(self) -> torch.Tensor:
+        """Make every parameter a view of ONE flat fp32 CUDA buffer in the library's canonical layout
+        (bdiff_param_layout), so the training pass reads the live weights with no per-step upload.  Idempotent; values
+        are preserved.  Call it (or run one training forward) BEFORE handing the parameters to an optimiser that records
+        their storage (GCDMTrainTail re-reads the pointers on its own)."""
+        lib = _lib.load()
+        h = self._ensure_handle()
+        params = list(self.named_parameters())
+        dev = params[0][1].device
+        if dev.type != "cuda":
+            raise _lib.BdiffError("GCPNetDynamicsB200 parameters must be on a CUDA device (no CPU fallback)")
+        if self._layout is None:
+            lay = {}
+            for name, _ in params:
+                off, cnt = C.c_int64(), C.c_int64()
+                _lib.check(h, lib.bdiff_param_layout(h, name.encode(), C.byref(off), C.byref(cnt)), f"bdiff_param_layout({name})")
+                lay[name] = (int(off.value), int(cnt.value))
+            self._layout = lay
+        total = int(lib.bdiff_param_floats(h))
+        if self._flat is None or self._flat.device != dev:
+            self._flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            self._grad_flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        base = self._flat.data_ptr()
+        with torch.no_grad():
+            for name, p in params:
+                off, cnt = self._layout[name]
+                if cnt != p.numel():
+                    raise _lib.BdiffError(f"parameter {name}: {p.numel()} elements, the library expects {cnt}")
+                if p.data_ptr() != base + 4 * off or p.dtype != torch.float32:
+                    view = self._flat[off:off + cnt].view(p.shape)
+                    view.copy_(p.detach())
+                    p.data = view
+        return self._flat
+
+    def _inputs(self, n: int, xh, t, context):
+        xh_c = xh.detach().to(torch.float32).contiguous()
+        t_c = t.detach().to(torch.float32).reshape(-1).contiguous()
+        if t_c.numel() == 1:
+            t_c = t_c.expand(n).contiguous()
+        if xh_c.shape != (n, 3 + self.cfg.num_h) or t_c.shape[0] != n:
+            raise ValueError(f"xh must be [{n},{3 + self.cfg.num_h}] and t [{n},1]")
+        ctx_c = None
+        if self.cfg.num_context:
+            if context is None:
+                raise ValueError("this configuration is property-conditional: batch.props_context is required")
+            ctx_c = context.detach().to(torch.float32).reshape(n, self.cfg.num_context).contiguous()
+        return xh_c, t_c, ctx_c
+
+    def _train_forward(self, batch_index, mask, xh, t, context, num_mols):
+        if not xh.is_cuda:
+            raise _lib.BdiffError("GCPNetDynamicsB200 runs on CUDA tensors only (no CPU fallback)")
+        lib = _lib.load()
+        flat = self.flatten_parameters()
+        _, n, _ = self.plan(batch_index, mask, num_mols)
+        xh_c, t_c, ctx_c = self._inputs(n, xh, t, context)
+        out = torch.empty_like(xh_c)
+        _lib.check(self._handle, lib.bdiff_train_forward(
+            self._handle, self._stream(), C.c_void_p(flat.data_ptr()), C.c_void_p(xh_c.data_ptr()),
+            C.c_void_p(t_c.data_ptr()), C.c_void_p(ctx_c.data_ptr()) if ctx_c is not None else None,
+            C.c_void_p(out.data_ptr())), "bdiff_train_forward")
+        self._tape_id += 1
+        return out
+
+    def _train_backward(self, d_out: torch.Tensor):
+        lib = _lib.load()
+        d = d_out.detach().to(torch.float32).contiguous()
+        _lib.check(self._handle, lib.bdiff_train_backward(self._handle, self._stream(), C.c_void_p(d.data_ptr()),
+                                                          C.c_void_p(self._grad_flat.data_ptr())), "bdiff_train_backward")
+        g = self._grad_flat.clone()        # autograd may keep / accumulate into what we return; the flat buffer is reused
+        out = []
+        for name, p in self.named_parameters():
+            off, cnt = self._layout[name]
+            out.append(g[off:off + cnt].view(p.shape))
+        return out
+
+    def denoise_train(self, batch_index: torch.Tensor, mask: torch.Tensor, xh: torch.Tensor, t: torch.Tensor,
+                      context: Optional[torch.Tensor] = None, num_mols: Optional[int] = None) -> torch.Tensor:
+        """`denoise` with a grad_fn: fp32 training pass of the library (one tape at a time)."""
+        return _DenoiseTrainFn.apply(self, batch_index, mask, xh, t, context, num_mols, *self.parameters())
+
+    def set_train_precision(self, tf32: bool) -> None:
+        """GEMMs of the training pass: fp32 (default) or TF32 tensor cores."""
+        lib = _lib.load()
+        _lib.check(self._ensure_handle(), lib.bdiff_train_precision(self._ensure_handle(), int(bool(tf32))), "bdiff_train_precision")
 
     def profile_forward(self, batch_index, mask, xh, t, context=None, num_mols=None):
         """One eager forward with CUDA events around every kernel class (inside the library, on the launch

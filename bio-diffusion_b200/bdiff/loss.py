@@ -5,8 +5,9 @@ src/models/components/variational_diffusion.py:955-1160 with :501-556, :598-699,
 evaluation branch of the Lightning module's assembly (src/models/qm9_mol_gen_ddpm.py:184-262): two denoiser calls
 (t ~ U{1..T} and t = 0) through libbdiff_sm100, the scalar bookkeeping in torch on the same device.
 `GCDMTrainLoss` is the training-mode L2 objective of the same function (one denoiser call, t ~ U{0..T}, L0 selected
-by the t == 0 mask; :979-980,985,1054-1055,1068-1069,1083-1103 and qm9_mol_gen_ddpm.py:232-245) — the VALUE only: the
-backward pass through the denoiser is not implemented.
+by the t == 0 mask; :979-980,985,1054-1055,1068-1069,1083-1103 and qm9_mol_gen_ddpm.py:232-245).  Called with autograd
+enabled and trainable parameters it runs the library's training pass, so `loss.mean().backward()` fills `p.grad` of
+every denoiser parameter; under no_grad / inference_mode it is the value only.
 """
 from __future__ import annotations
 
@@ -35,8 +36,11 @@ class GCDMEvalNLL:
         prob = torch.tensor([float(n_nodes_histogram[k]) for k in n_nodes_histogram.keys()])
         self.log_pn = torch.log(prob / prob.sum() + 1e-30)           # NumNodesDistribution (models/__init__.py:264-308)
 
-    @torch.inference_mode()
-    def __call__(self, batch_index: torch.Tensor, mask: torch.Tensor, x: torch.Tensor, one_hot: torch.Tensor,
+    def __call__(self, *args, **kwargs):
+        with torch.inference_mode():
+            return self._impl(*args, **kwargs)
+
+    def _impl(self, batch_index: torch.Tensor, mask: torch.Tensor, x: torch.Tensor, one_hot: torch.Tensor,
                  charges: torch.Tensor, context: Optional[torch.Tensor] = None, t_int: Optional[torch.Tensor] = None,
                  noise: Optional[NoiseFn] = None, training: bool = False, norm_training_by_max_nodes: bool = False):
         """x [N,3] (CoG-free), one_hot [N,A], charges [N] (or [N,0] without charges), context [N,C] or None.
@@ -85,7 +89,8 @@ class GCDMEvalNLL:
         sigma = lambda g: torch.sqrt(torch.sigmoid(g))
         eps_t = centered_noise()
         z_t = alpha(g_t)[batch_index] * xh + sigma(g_t)[batch_index] * eps_t
-        net_out = self.net.denoise(batch_index, mask, z_t, t[batch_index], context, nmol)
+        denoise = self.net.denoise_train if self.net.wants_grad() else self.net.denoise
+        net_out = denoise(batch_index, mask, z_t, t[batch_index], context, nmol)
         error_t = seg_sum((eps_t - net_out) ** 2)
         snr_weight = (torch.exp(-(g_s - g_t)) - 1).squeeze(-1)
         g0, g_T = gamma[0], gamma[T]
@@ -136,9 +141,12 @@ class GCDMEvalNLL:
 
 
 class GCDMTrainLoss(GCDMEvalNLL):
-    """Training-mode objective (loss_type "l2"): `loss, terms = GCDMTrainLoss(net, histogram)(batch_index, mask, x, ...)`.
-    Forward value only (inference mode); see the module docstring."""
+    """Training-mode objective (loss_type "l2"): `loss, terms = GCDMTrainLoss(net, histogram)(batch_index, mask, x, ...)`;
+    `loss.mean().backward()` is the reference's training_step (qm9_mol_gen_ddpm.py:340-362).  With autograd disabled (or
+    no trainable parameter) the value is computed by the sampler kernels in inference mode."""
 
     def __call__(self, *args, **kwargs):
         kwargs.setdefault("training", True)
+        if self.net.wants_grad():
+            return self._impl(*args, **kwargs)
         return super().__call__(*args, **kwargs)

@@ -52,7 +52,19 @@ class GCDMTrainTail:
         self.ema = [p.detach().clone() for p in self.params]
         for p, g in zip(self.params, self.grads):
             p.grad = g
+        self._build_table()
+        st = np.zeros(STATE_WORDS, dtype=np.int32)
+        st[1] = 1                                   # history seeded with one entry of 3000 (qm9_mol_gen_ddpm.py:148-149)
+        st[2] = 1 % queue_len
+        st[8:9] = np.array([3000.0], dtype=np.float32).view(np.int32)
+        self.state = torch.from_numpy(st).to(dev)
+        self.kernel_launches = 0
+
+    def _build_table(self):
+        """Device-side pointer table; rebuilt if a parameter's storage moved (GCPNetDynamicsB200.flatten_parameters)."""
+        dev, amsgrad = self.device, self.max_exp_avg_sq is not None
         chunk = int(self.lib.bdiff_optimizer_chunk())
+        self._ptrs = [p.data_ptr() for p in self.params]
         rec = np.zeros((len(self.params), 7), dtype=np.int64)
         ct, cs = [], []
         for i, p in enumerate(self.params):
@@ -65,12 +77,6 @@ class GCDMTrainTail:
         self.chunk_tensor = torch.tensor(ct, dtype=torch.int32, device=dev)
         self.chunk_start = torch.tensor(cs, dtype=torch.int64, device=dev)
         self.partial = torch.zeros(len(ct), dtype=torch.float64, device=dev)
-        st = np.zeros(STATE_WORDS, dtype=np.int32)
-        st[1] = 1                                   # history seeded with one entry of 3000 (qm9_mol_gen_ddpm.py:148-149)
-        st[2] = 1 % queue_len
-        st[8:9] = np.array([3000.0], dtype=np.float32).view(np.int32)
-        self.state = torch.from_numpy(st).to(dev)
-        self.kernel_launches = 0
 
     def zero_grad(self):
         for g in self.grads:
@@ -80,6 +86,8 @@ class GCDMTrainTail:
         for p, g in zip(self.params, self.grads):
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                 raise _lib.BdiffError("p.grad was replaced; keep the buffers GCDMTrainTail installed (use opt.zero_grad())")
+        if any(p.data_ptr() != q for p, q in zip(self.params, self._ptrs)):
+            self._build_table()
         rc = self.lib.bdiff_optimizer_step(
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream), C.c_void_p(self.table.data_ptr()),
             C.c_void_p(self.chunk_tensor.data_ptr()), C.c_void_p(self.chunk_start.data_ptr()),

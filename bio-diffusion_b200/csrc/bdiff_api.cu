@@ -11,7 +11,7 @@
 #include <vector>
 
 #include "../../include/bdiff.h"
-#include "bdiff_kernels.h"
+#include "bdiff_handle.h"
 
 using namespace bdiff;
 
@@ -19,89 +19,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t ensure(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&p, need);
-    if (e != cudaSuccess) return e;
-    bytes = need;
-    return cudaMemset(p, 0, need);
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-};
-
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
-
-struct bdiff_handle {
-  bdiff_config cfg{};
-  Dims d{};
-  std::string err;
-  int64_t launches = 0;
-
-  // packed weights
-  float* wbuf = nullptr;
-  size_t wfloats = 0, wused = 0;
-  std::vector<LayerW> layers;
-  EmbedW embed{};
-  std::map<std::string, bool> seen;   // reference parameter name -> set?
-  // raw copies of the reference tensors + the slice table: all slices are repacked by ONE kernel in bdiff_prepare
-  DevBuf stage_buf, jobs_dev;
-  size_t stage_used = 0;
-  std::map<std::string, size_t> stage_off;      // parameter name -> offset (floats) of its raw copy
-  std::vector<PackJob> jobs;
-  int pack_blocks = 0;
-  bool pack_dirty = false, jobs_uploaded = false;
-
-  // plan
-  bool have_plan = false;
-  Plan plan{};
-  DevBuf plan_buf, rc_buf, layers_dev, sched_buf, items_buf;
-  LayerSched sched{};
-  int Npad = 0;
-  long long Epad = 0;
-
-  // workspace
-  DevBuf work_buf;
-  Work work{};
-  DevBuf eps_buf;      // [N,3+F] denoiser output inside reverse_step / decode
-  DevBuf dbg_buf;      // clock64 stamps (BDIFF_TIMING=1)
-  DevBuf tu_buf;       // uniform t scalar
-
-  // tensor-core path state (bdiff_edge_tc.cu): per-layer pre-swizzled bf16 weight blobs
-  DevBuf tc_blob, tc_node_blob;
-  size_t tc_layer_bytes = 0, tc_node_layer_bytes = 0;
-  bool tc_dirty = true;
-  int num_sms = 148;
-  cudaStream_t side = nullptr;          // fork/join stream: the edge embedding runs next to the node embedding
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-
-  int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    err = buf;
-    return code;
-  }
-  float* walloc(size_t n) {
-    n = (n + 63) / 64 * 64;   // 256-byte granularity keeps every matrix 16 B aligned for bulk copies
-    float* r = wbuf + wused;
-    wused += n;
-    return r;
-  }
-};
 
 namespace {
 
@@ -335,6 +254,14 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
     gcp_names(h->seen, p + "feedforward_network.0.", true, true);
     gcp_names(h->seen, p + "node_position_update_gcp.", false, true);
   }
+  for (auto& kv : h->seen) {
+    std::vector<PackOp> ops;
+    int64_t rows = 0, cols = 0;
+    if (!resolve(h, kv.first, ops, rows, cols)) { g_create_error = "internal: cannot place " + kv.first; cudaFree(h->wbuf); delete h; return BDIFF_EINVAL; }
+    const size_t count = (size_t)rows * (size_t)cols;
+    h->param_layout[kv.first] = {h->param_floats, count};
+    h->param_floats += (count + 63) / 64 * 64;
+  }
   h->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -368,6 +295,7 @@ int32_t bdiff_create(const bdiff_config* cfg, bdiff_handle** out) {
 void bdiff_destroy(bdiff_handle* h) {
   if (!h) return;
   if (h->wbuf) cudaFree(h->wbuf);
+  if (h->train) train_destroy(h->train);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
@@ -665,6 +593,8 @@ int32_t bdiff_plan_topology(bdiff_handle* h, void* stream, int32_t num_mols, int
   e = ensure_work(h);
   if (e != cudaSuccess) return h->fail(BDIFF_ENOMEM, "workspace: %s", cudaGetErrorString(e));
   h->have_plan = true;
+  h->plan_epoch++;
+  h->Mact = (int)M;
   if (num_edges_host) *num_edges_host = E;
   return BDIFF_OK;
 }

@@ -233,6 +233,32 @@ BDIFF_API int32_t bdiff_prepare_context(void* stream, const float* props, const 
                                         const float* mean, const float* mad, int64_t dataset_size, int64_t num_nodes,
                                         int32_t num_props, float* context);
 
+/* ---- training pass of the denoiser ---------------------------------------------------------------
+ * Replaces: loss.backward() through GCPNetDynamics.forward (src/models/components/gcpnet.py:1069-1232) inside
+ * EquivariantVariationalDiffusion.forward in .train() mode (variational_diffusion.py:955-1160) — what the Lightning
+ * training_step triggers (src/models/qm9_mol_gen_ddpm.py:340-362).
+ *
+ * Parameters and gradients travel as ONE flat fp32 buffer each, in a canonical layout: the reference tensors (same
+ * names and shapes as bdiff_set_weight, nn.Linear weights [out,in] row-major) in ascending name order, each starting at
+ * a multiple of 64 floats.  bdiff_param_floats = length of such a buffer; bdiff_param_layout = {offset, count} of one
+ * tensor.  A host keeps its nn.Parameters as views of the flat parameter buffer (bdiff/dynamics.py does), so an
+ * optimiser step needs no re-upload.
+ *
+ * bdiff_train_forward: net_out = denoiser(params_flat; xh, t, context) on the current topology plan, same arguments and
+ *   result as bdiff_denoise_forward (fp32), and keeps every intermediate the derivative needs (the "tape", device memory
+ *   owned by the handle; one tape at a time).
+ * bdiff_train_backward: grads_flat <- d/dparams sum(net_out * d_net_out) for the tape of the last bdiff_train_forward
+ *   (the buffer is overwritten, not accumulated into).  No atomics: results are bit-reproducible.
+ * bdiff_train_precision: tf32 = 0 (default) fp32 GEMMs, 1 = TF32 tensor-core GEMMs (the reference's bf16-mixed training
+ *   configuration is the looser of the two).
+ * All on `stream`, no host synchronisation.  Errors: BDIFF_ESTATE without a plan / tape, BDIFF_ENOMEM for the tape. */
+BDIFF_API int64_t bdiff_param_floats(const bdiff_handle* h);
+BDIFF_API int32_t bdiff_param_layout(bdiff_handle* h, const char* name, int64_t* offset, int64_t* count);
+BDIFF_API int32_t bdiff_train_precision(bdiff_handle* h, int32_t tf32);
+BDIFF_API int32_t bdiff_train_forward(bdiff_handle* h, void* stream, const float* params_flat, const float* xh, const float* t,
+                                      const float* context, float* net_out);
+BDIFF_API int32_t bdiff_train_backward(bdiff_handle* h, void* stream, const float* d_net_out, float* grads_flat);
+
 /* Replaces: the warn-and-zero NaN guard of gcpnet.py:1214-1216 as an observable.  *count_host <- number of denoiser
  * forwards (since the last reset / re-plan of the workspace) in which a NaN position appeared and `vel` was zeroed.
  * Synchronises `stream`.  bench.py reports it for every timed chain. */

@@ -87,9 +87,10 @@ def test_forward_drop_in_contract():
     with torch.no_grad():
         net(b, xh, fx["t"].cuda())
     assert net._plan_key == key
-    # under autograd with trainable parameters the module refuses loudly instead of returning a detached output
-    with pytest.raises(NotImplementedError):
-        net(b, xh, fx["t"].cuda())
+    # under autograd with trainable parameters the module runs the training pass: the output carries a grad_fn instead of
+    # being silently detached; tests/test_gpu_train.py checks the gradients
+    _, out_g = net(b, xh, fx["t"].cuda())
+    assert out_g.grad_fn is not None and relerr(out_g.detach().cpu(), fx["net_out"]) <= 5e-5
 
 
 def test_forward_is_deterministic_and_batch_composable():
@@ -239,17 +240,22 @@ def test_eval_nll_on_device_matches_reference(name):
     assert torch.allclose(nll.cpu(), fx["nll"], rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("autograd", [False, True])
 @pytest.mark.parametrize("name", ["train_qm9", "train_geom"])
-def test_training_loss_on_device_matches_reference(name):
+def test_training_loss_on_device_matches_reference(name, autograd):
     """GCDMTrainLoss (one denoiser call through the C ABI, t == 0 molecule included) vs the reference in .train() mode;
-    the fixture's t_int and CPU noise stream are replayed; tolerance 1e-4 relative on every term and on the loss."""
+    the fixture's t_int and CPU noise stream are replayed; tolerance 1e-4 relative on every term and on the loss.
+    autograd=False: value from the sampler kernels; True: from the training pass (loss carries a grad_fn)."""
     import bdiff
     fx = load_golden(name)
     net, ocfg, sd = make_net(fx["config"], fx["weight_seed"], scale=fx["weight_scale"])
     tl = bdiff.GCDMTrainLoss(net, fx["histogram"])
     torch.manual_seed(fx["rng_seed"])
-    loss, terms = tl(fx["batch_index"].cuda(), fx["mask"].cuda(), fx["x"].cuda(), fx["one_hot"].cuda(),
-                     fx["charges"].cuda(), None, t_int=fx["terms"]["t_int"].reshape(-1, 1), noise=lambda s: torch.randn(s))
+    with torch.set_grad_enabled(autograd):
+        loss, terms = tl(fx["batch_index"].cuda(), fx["mask"].cuda(), fx["x"].cuda(), fx["one_hot"].cuda(),
+                         fx["charges"].cuda(), None, t_int=fx["terms"]["t_int"].reshape(-1, 1), noise=lambda s: torch.randn(s))
+    assert loss.requires_grad == autograd
+    loss, terms = loss.detach(), {k: v.detach() for k, v in terms.items()}
     for k, ref in fx["terms"].items():
         if k == "t_int":
             continue
