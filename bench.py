@@ -661,7 +661,7 @@ def run_train(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         # the same objective on the host: autograd through the oracle port, first `cpu_mols` molecules of batch 0
-        cpu_mols = 4
+        cpu_mols = 32
         bi, mask, x, one_hot, charges = batches[0]
         nn0 = int((bi < cpu_mols).sum())
         sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
