@@ -48,6 +48,7 @@ struct TrainState {
   const float* params = nullptr;
   float* grads = nullptr;
   bool tf32 = false;
+  int variant = 0, laid_variant = -1;
 };
 
 void train_destroy(TrainState* t) {
@@ -72,7 +73,9 @@ int32_t ensure_train(bdiff_handle* h, cudaStream_t st, const float* params, floa
   }
   cublasSetStream(t->be.cb, st);
   t->be.st = st;
-  if (t->plan_epoch == h->plan_epoch && t->params == params && (grads == nullptr || t->grads == grads)) return BDIFF_OK;
+  if (t->plan_epoch == h->plan_epoch && t->params == params && (grads == nullptr || t->grads == grads) &&
+      t->laid_variant == t->variant)
+    return BDIFF_OK;
   train::NetDims d{h->d.F, h->d.C, h->d.Hin, h->d.Ed, h->d.Xd, h->d.L};
   train::Topo tp;
   const Plan& p = h->plan;
@@ -86,7 +89,9 @@ int32_t ensure_train(bdiff_handle* h, cudaStream_t st, const float* params, floa
     if (it == h->param_layout.end()) { ++missing; return train::ParamRef{params, g}; }
     return train::ParamRef{params + it->second.first, g ? g + it->second.first : nullptr};
   };
-  const bool same_shape = t->plan_epoch == h->plan_epoch;
+  const bool same_shape = t->plan_epoch == h->plan_epoch && t->laid_variant == t->variant;
+  t->eng.variant = t->variant;
+  t->laid_variant = t->variant;
   if (!same_shape) {
     const size_t need = t->eng.layout(d, tp, nullptr, look);
     if (missing) return h->fail(BDIFF_ESTATE, "internal: %d parameter names unknown to the training pass", missing);
@@ -141,6 +146,14 @@ int32_t bdiff_train_precision(bdiff_handle* h, int32_t tf32) {
   return BDIFF_OK;
 }
 
+int32_t bdiff_train_variant(bdiff_handle* h, int32_t variant) {
+  if (!h) return BDIFF_EINVAL;
+  if (variant != 0 && variant != 1) return h->fail(BDIFF_EINVAL, "training variant must be 0 or 1");
+  if (!h->train) h->train = new TrainState();
+  h->train->variant = variant;
+  return BDIFF_OK;
+}
+
 int32_t bdiff_train_forward(bdiff_handle* h, void* stream, const float* params_flat, const float* xh, const float* t,
                             const float* context, float* net_out) {
   if (!h || !params_flat || !xh || !t || !net_out) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
@@ -154,7 +167,7 @@ int32_t bdiff_train_forward(bdiff_handle* h, void* stream, const float* params_f
 
 int32_t bdiff_train_backward(bdiff_handle* h, void* stream, const float* d_net_out, float* grads_flat) {
   if (!h || !d_net_out || !grads_flat) return h ? h->fail(BDIFF_EINVAL, "null argument") : BDIFF_EINVAL;
-  if (!h->train || !h->train->eng.have_tape || h->train->plan_epoch != h->plan_epoch)
+  if (!h->train || !h->train->eng.have_tape || h->train->plan_epoch != h->plan_epoch || h->train->laid_variant != h->train->variant)
     return h->fail(BDIFF_ESTATE, "bdiff_train_backward needs the tape of a bdiff_train_forward on the current plan");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TrainState* t = h->train;

@@ -189,9 +189,11 @@ struct FBiasSilu {      // feed-forward scalar_out: z1 += b0 (kept), a = silu(z1
 struct FScalarOut {     // z += bias (kept on the tape); s_out = (act0(z) + residual) * mask; a1 = act1(z)
   float* z; const float* b; int n, act0, act1;
   float* s_out; int ld_so; const float* res; int ld_res; const unsigned char* mask; float* a1;
+  const float *pi, *pj; const EdgeRc* rc;     // split message GCP 0: z += PI[row] + PJ[col] (node-level h.Wsi^T, h.Wsj^T)
   BDT_HD void operator()(long long idx) const {
     const long long m = idx / n; const int j = (int)(idx % n);
-    const float zz = z[idx] + b[j];
+    float zz = z[idx] + b[j];
+    if (pi) zz += pi[(long long)rc[m].row * n + j] + pj[(long long)rc[m].col * n + j];
     z[idx] = zz;
     if (a1) a1[idx] = t_act(act1, zz);
     if (s_out) {
@@ -410,6 +412,22 @@ struct FScatterV {
     dchi[nx * ld + o] += acc;
   }
 };
+struct FScatterDZ {     // split message GCP 0: dPI[n] = sum over row n of dz, dPJ[n] = sum over column n of dz
+  Topo tp; const int* apos; const float* dz; float *dpi, *dpj;
+  BDT_HD void operator()(long long idx) const {
+    const long long n = idx / 256; const int j = (int)(idx % 256);
+    long long e0; int na;
+    row_span(tp, apos, n, e0, na);
+    float a0 = 0.f, a1 = 0.f;
+    if (na) {
+      for (int b = 0; b < na; ++b) a0 += dz[(e0 + b) * 256 + j];
+      const int a = apos[n];
+      const long long base = e0 - (long long)a * na;
+      for (int r = 0; r < na; ++r) a1 += dz[(base + (long long)r * na + a) * 256 + j];
+    }
+    dpi[idx] = a0; dpj[idx] = a1;
+  }
+};
 struct FMaskAdd {       // dst[m, c] = (dst[m, c] + add[m_row, c]) * mask[m]; rows_per = 1 (scalars) or 3 (vectors)
   float* dst; int ld_d; const float* add; int ld_a, cols, rows_per; const unsigned char* mask;
   BDT_HD void operator()(long long idx) const {
@@ -461,7 +479,13 @@ struct Gcp {
   float *gWd = nullptr, *gWf = nullptr, *gWs = nullptr, *gbs = nullptr, *gW2 = nullptr, *gb2 = nullptr, *gWu = nullptr,
         *gWg = nullptr, *gbg = nullptr;
   float* vt = nullptr; int ldv = 0;    // input vectors [M*3, ldv]
-  float* merged = nullptr; int fan = 0;
+  float* merged = nullptr; int fan = 0; // [M, fan] = [s | vnorm | q]; the scalar_out weight block that multiplies it starts at
+  int fanW = 0, wcol = 0;               // column wcol of Ws, whose rows are fanW long (fanW = fan, wcol = 0 unless split)
+  // split form of message GCP 0 (variant 1): merged = [vnorm | q] only; z also gets e.We^T (a second GEMM) and the
+  // node-level projections PI[row] + PJ[col] (gathered in FScalarOut)
+  int split = 0, Ed = 0;
+  const float *ee = nullptr, *pi = nullptr, *pj = nullptr; const EdgeRc* rc = nullptr;
+  float *a1t = nullptr, *aff = nullptr;  // variant 1: act1(z) and silu(z1) kept on the tape instead of recomputed
   float *hid = nullptr, *vdf = nullptr, *z1 = nullptr, *z = nullptr, *up = nullptr, *sg = nullptr;
   const float* frames = nullptr;        // [M, 9]: edge frames or the nodes' mean row frames
 };
@@ -471,6 +495,16 @@ struct Scratch {        // sized for the largest entity count; used inside one G
 };
 
 struct ParamRef { const float* w; float* g; };
+
+// Where a GCP's backward puts its input gradients.  Variant 0: `dmerged` [M, fan] gets d[s | vnorm | q] from one GEMM.
+// Variant 1 (`dvq` set): d s goes straight to its consumer (`ds_dst`, = or +=, skipped when null) and only d[vnorm | q]
+// [M, H+9] is materialised.
+struct BwdOut {
+  float* dmerged = nullptr;
+  float* ds_dst = nullptr; int ld_ds = 0; float beta_ds = 0.f;
+  float* dvq = nullptr;
+  float* dvt = nullptr; int ld_dvt = 0; float beta_dvt = 0.f;
+};
 
 // Everything below is host code (both backends).
 template <class Backend>
@@ -507,6 +541,9 @@ struct Engine {
   float *DX = nullptr, *DHP = nullptr, *DH = nullptr, *DCHI = nullptr, *DMN = nullptr, *DFV = nullptr, *DME = nullptr,
         *DMV = nullptr, *DS = nullptr, *DV = nullptr, *DPRE = nullptr, *DE = nullptr, *DXI = nullptr, *DEV = nullptr;
   Scratch sc{};
+  int variant = 0;              // 0: the straightforward graph; 1: split message GCP 0, activations on the tape, input
+                                // gradients written straight to their consumers (set before layout())
+  float *PI = nullptr, *PJ = nullptr, *DVQ = nullptr;
   float* grad_base = nullptr;   // flat gradient buffer (reference layout), zeroed at the start of backward()
   size_t grad_count = 0;
   bool have_tape = false;
@@ -515,10 +552,12 @@ struct Engine {
 
   template <class Lookup>
   void shape_gcp(Gcp& g, const std::string& p, long long M, int S_in, int V_in, int S_out, int V_out, int bott, int ff,
-                 int act, const float* fr, Lookup& look) {
+                 int act, const float* fr, Lookup& look, int split = 0) {
     g.M = M; g.S_in = S_in; g.V_in = V_in; g.S_out = S_out; g.V_out = V_out; g.ff = ff; g.act0 = act; g.act1 = act;
     g.H = hid_of(V_in, V_out, bott);
     g.fan = S_in + g.H + 9;
+    g.fanW = g.fan; g.wcol = 0; g.split = split;
+    if (split) { g.wcol = S_in; g.S_in = 0; g.fan = g.H + 9; }
     g.frames = fr;
     auto P = [&](const char* leaf, const float*& w, float*& gr) { ParamRef r = look(p + leaf); w = r.w; gr = r.g; };
     P("vector_down.weight", g.Wd, g.gWd);
@@ -540,6 +579,8 @@ struct Engine {
     g.z = take((size_t)M * S_out);
     g.up = V_out ? take((size_t)M * 3 * V_out) : nullptr;
     g.sg = V_out ? take((size_t)M * V_out) : nullptr;
+    g.a1t = (variant && V_out) ? take((size_t)M * S_out) : nullptr;
+    g.aff = (variant && ff) ? take((size_t)M * S_out) : nullptr;
   }
 
   // Lays out the tape for (dims, topology sizes).  Call with assign=false to size the arena, then with the arena.
@@ -561,8 +602,9 @@ struct Engine {
     for (int l = 0; l < d.L; ++l) {
       Layer& y = layers[l];
       const std::string p = "interaction_layers." + std::to_string(l) + ".";
-      shape_gcp(y.msg[0], p + "interaction.message_fusion.0.", E, 512 + d.Ed, 64 + d.Xd, 256, 32, 4, 0, 1, frames, look);
+      shape_gcp(y.msg[0], p + "interaction.message_fusion.0.", E, 512 + d.Ed, 64 + d.Xd, 256, 32, 4, 0, 1, frames, look, variant);
       y.msg[0].vt = take((size_t)E * 3 * (64 + d.Xd)); y.msg[0].ldv = 64 + d.Xd;
+      y.msg[0].Ed = d.Ed; y.msg[0].ee = EE; y.msg[0].rc = tp.edge_rc;
       for (int k = 0; k < 4; ++k) y.V[k] = take((size_t)E * 96);
       for (int k = 1; k < 4; ++k) {
         shape_gcp(y.msg[k], p + "interaction.message_fusion." + std::to_string(k) + ".", E, 256, 32, 256, 32, 4, 0, 1, frames, look);
@@ -588,6 +630,8 @@ struct Engine {
     DME = take((size_t)E * (512 + d.Ed + (64 + d.Xd) / 4 + 9)); DMV = take((size_t)E * 3 * (64 + d.Xd));
     DS = take((size_t)E * 256); DV = take((size_t)E * 96); DPRE = take((size_t)E);
     DE = take((size_t)E * d.Ed); DXI = take((size_t)E * 3 * d.Xd); DEV = take((size_t)E * 3);
+    PI = take((size_t)N * 256); PJ = take((size_t)N * 256); DVQ = take((size_t)Mx * 48);
+    for (int l = 0; l < d.L; ++l) { layers[l].msg[0].pi = PI; layers[l].msg[0].pj = PJ; }
     have_tape = false;
     return used;
   }
@@ -607,34 +651,38 @@ struct Engine {
     be.gemm(false, true, M * 3, 3, g.V_in, g.vt, g.ldv, g.Wf, g.V_in, g.vdf, 3, 0.f);              // vector_down_frames
     be.run(M * (g.H + 9), FMerge{g.hid, g.vdf, g.frames, g.merged, g.S_in, g.H, g.fan});
     const float* bias = g.bs;
+    const float* Wm = g.Ws + g.wcol;      // the block of scalar_out's weight that multiplies `merged`
+    float* a1 = g.a1t ? g.a1t : sc.a1;
     if (g.ff) {
-      be.gemm(false, true, M, g.S_out, g.fan, g.merged, g.fan, g.Ws, g.fan, g.z1, g.S_out, 0.f);
-      be.run(M * g.S_out, FBiasSilu{g.z1, g.bs, sc.a1, g.S_out});
-      be.gemm(false, true, M, g.S_out, g.S_out, sc.a1, g.S_out, g.W2, g.S_out, g.z, g.S_out, 0.f);
+      float* a = g.aff ? g.aff : sc.a1;
+      be.gemm(false, true, M, g.S_out, g.fan, g.merged, g.fan, Wm, g.fanW, g.z1, g.S_out, 0.f);
+      be.run(M * g.S_out, FBiasSilu{g.z1, g.bs, a, g.S_out});
+      be.gemm(false, true, M, g.S_out, g.S_out, a, g.S_out, g.W2, g.S_out, g.z, g.S_out, 0.f);
       bias = g.b2;
     } else {
-      be.gemm(false, true, M, g.S_out, g.fan, g.merged, g.fan, g.Ws, g.fan, g.z, g.S_out, 0.f);
+      be.gemm(false, true, M, g.S_out, g.fan, g.merged, g.fan, Wm, g.fanW, g.z, g.S_out, 0.f);
+      if (g.split) be.gemm(false, true, M, g.S_out, g.Ed, g.ee, g.Ed, g.Ws + 256, g.fanW, g.z, g.S_out, 1.f);   // + e.We^T
     }
     be.run(M * g.S_out, FScalarOut{g.z, bias, g.S_out, g.act0, g.act1, s_out, ld_so, res_s, ld_rs, mask,
-                                   g.V_out ? sc.a1 : nullptr});
+                                   g.V_out ? a1 : nullptr, g.split ? g.pi : nullptr, g.pj, g.rc});
     if (!g.V_out) return;
     be.gemm(false, true, M * 3, g.V_out, g.H, g.hid, g.H, g.Wu, g.H, g.up, g.V_out, 0.f);           // vector_up
-    be.gemm(false, true, M, g.V_out, g.S_out, sc.a1, g.S_out, g.Wg, g.S_out, g.sg, g.V_out, 0.f);   // vector_out_scale
+    be.gemm(false, true, M, g.V_out, g.S_out, a1, g.S_out, g.Wg, g.S_out, g.sg, g.V_out, 0.f);      // vector_out_scale
     be.run(M * g.V_out, FVecOut{g.sg, g.bg, g.up, g.V_out, v_out, ld_vo, res_v, ld_rv, mask});
   }
 
   // ---------------------------------------------------------------------------------------------- GCP backward
-  // (d s_out [M, ld_ds] or null, d v_out [M*3, ld_dv] or null) -> dmerged [M, fan] (its first S_in columns are d s)
-  // and, if dvt != null, d v [M*3, ld_dvt] (= or +=).  Parameter gradients are accumulated.
-  void gcp_backward(Gcp& g, const float* ds_out, int ld_ds, const float* dv_out, int ld_dv, float* dmerged, float* dvt,
-                    int ld_dvt, float beta_dvt) {
+  // (d s_out [M, ld_ds] or null, d v_out [M*3, ld_dv] or null) -> input gradients as `o` says (see BwdOut).  Parameter
+  // gradients are accumulated.  On return sc.dz (ff: sc.dgz) still holds d z of the scalar_out linear map.
+  void gcp_backward(Gcp& g, const float* ds_out, int ld_ds, const float* dv_out, int ld_dv, const BwdOut& o) {
     const long long M = g.M;
     if (M == 0) return;
     const float* dgz = nullptr;
     if (g.V_out) {
       be.run(M * g.V_out, FDVecOut{dv_out, g.up, g.sg, ld_dv, g.V_out, sc.dg, sc.dup});
-      be.run(M * g.S_out, FAct{g.z, sc.a1, g.act1});
-      be.gemm(true, false, g.V_out, g.S_out, M, sc.dg, g.V_out, sc.a1, g.S_out, g.gWg, g.S_out, 1.f);
+      const float* a1 = g.a1t;
+      if (!a1) { be.run(M * g.S_out, FAct{g.z, sc.a1, g.act1}); a1 = sc.a1; }
+      be.gemm(true, false, g.V_out, g.S_out, M, sc.dg, g.V_out, a1, g.S_out, g.gWg, g.S_out, 1.f);
       colsum(sc.dg, M, g.V_out, g.V_out, g.gbg);
       be.gemm(false, false, M, g.S_out, g.V_out, sc.dg, g.V_out, g.Wg, g.S_out, sc.dgz, g.S_out, 0.f);
       be.gemm(true, false, g.V_out, g.H, M * 3, sc.dup, g.V_out, g.hid, g.H, g.gWu, g.H, 1.f);
@@ -642,28 +690,43 @@ struct Engine {
       dgz = sc.dgz;
     }
     be.run(M * g.S_out, FDZ{ds_out, ld_ds, dgz, g.z, g.S_out, g.act0, g.act1, sc.dz});
+    const float* dzz = sc.dz;             // gradient at the output of the linear map that reads `merged`
     if (g.ff) {
-      be.run(M * g.S_out, FAct{g.z1, sc.a1, 1});
-      be.gemm(true, false, g.S_out, g.S_out, M, sc.dz, g.S_out, sc.a1, g.S_out, g.gW2, g.S_out, 1.f);
+      const float* a = g.aff;
+      if (!a) { be.run(M * g.S_out, FAct{g.z1, sc.a1, 1}); a = sc.a1; }
+      be.gemm(true, false, g.S_out, g.S_out, M, sc.dz, g.S_out, a, g.S_out, g.gW2, g.S_out, 1.f);
       colsum(sc.dz, M, g.S_out, g.S_out, g.gb2);
       be.gemm(false, false, M, g.S_out, g.S_out, sc.dz, g.S_out, g.W2, g.S_out, sc.dgz, g.S_out, 0.f);
       be.run(M * g.S_out, FMulDSilu{sc.dgz, g.z1});
-      be.gemm(true, false, g.S_out, g.fan, M, sc.dgz, g.S_out, g.merged, g.fan, g.gWs, g.fan, 1.f);
-      colsum(sc.dgz, M, g.S_out, g.S_out, g.gbs);
-      be.gemm(false, false, M, g.fan, g.S_out, sc.dgz, g.S_out, g.Ws, g.fan, dmerged, g.fan, 0.f);
-    } else {
-      be.gemm(true, false, g.S_out, g.fan, M, sc.dz, g.S_out, g.merged, g.fan, g.gWs, g.fan, 1.f);
-      colsum(sc.dz, M, g.S_out, g.S_out, g.gbs);
-      be.gemm(false, false, M, g.fan, g.S_out, sc.dz, g.S_out, g.Ws, g.fan, dmerged, g.fan, 0.f);
+      dzz = sc.dgz;
     }
-    be.run(M * g.H, FDNorm{dmerged, g.fan, g.S_in, g.H, g.hid, sc.dhid, g.V_out ? 1 : 0});
-    be.run(M * 9, FDQ{dmerged, g.fan, g.S_in + g.H, g.frames, sc.dvdf});
+    be.gemm(true, false, g.S_out, g.fan, M, dzz, g.S_out, g.merged, g.fan, g.gWs + g.wcol, g.fanW, 1.f);
+    colsum(dzz, M, g.S_out, g.S_out, g.gbs);
+    const float* vq; int ldq, offq;
+    if (o.dvq) {
+      if (o.ds_dst && g.S_in)
+        be.gemm(false, false, M, g.S_in, g.S_out, dzz, g.S_out, g.Ws + g.wcol, g.fanW, o.ds_dst, o.ld_ds, o.beta_ds);
+      be.gemm(false, false, M, g.H + 9, g.S_out, dzz, g.S_out, g.Ws + g.wcol + g.S_in, g.fanW, o.dvq, g.H + 9, 0.f);
+      vq = o.dvq; ldq = g.H + 9; offq = 0;
+    } else {
+      be.gemm(false, false, M, g.fan, g.S_out, dzz, g.S_out, g.Ws + g.wcol, g.fanW, o.dmerged, g.fan, 0.f);
+      vq = o.dmerged; ldq = g.fan; offq = g.S_in;
+    }
+    be.run(M * g.H, FDNorm{vq, ldq, offq, g.H, g.hid, sc.dhid, g.V_out ? 1 : 0});
+    be.run(M * 9, FDQ{vq, ldq, offq + g.H, g.frames, sc.dvdf});
     be.gemm(true, false, 3, g.V_in, M * 3, sc.dvdf, 3, g.vt, g.ldv, g.gWf, g.V_in, 1.f);
     be.gemm(true, false, g.H, g.V_in, M * 3, sc.dhid, g.H, g.vt, g.ldv, g.gWd, g.V_in, 1.f);
-    if (dvt) {
-      be.gemm(false, false, M * 3, g.V_in, 3, sc.dvdf, 3, g.Wf, g.V_in, dvt, ld_dvt, beta_dvt);
-      be.gemm(false, false, M * 3, g.V_in, g.H, sc.dhid, g.H, g.Wd, g.V_in, dvt, ld_dvt, 1.f);
+    if (o.dvt) {
+      be.gemm(false, false, M * 3, g.V_in, 3, sc.dvdf, 3, g.Wf, g.V_in, o.dvt, o.ld_dvt, o.beta_dvt);
+      be.gemm(false, false, M * 3, g.V_in, g.H, sc.dhid, g.H, g.Wd, g.V_in, o.dvt, o.ld_dvt, 1.f);
     }
+  }
+  static BwdOut out0(float* dmerged, float* dvt, int ld_dvt, float beta_dvt) {
+    BwdOut o; o.dmerged = dmerged; o.dvt = dvt; o.ld_dvt = ld_dvt; o.beta_dvt = beta_dvt; return o;
+  }
+  BwdOut out1(float* ds_dst, int ld_ds, float beta_ds, float* dvt, int ld_dvt, float beta_dvt) {
+    BwdOut o; o.ds_dst = ds_dst; o.ld_ds = ld_ds; o.beta_ds = beta_ds; o.dvq = DVQ; o.dvt = dvt; o.ld_dvt = ld_dvt;
+    o.beta_dvt = beta_dvt; return o;
   }
 
   // ---------------------------------------------------------------------------------------------- network forward
@@ -686,7 +749,12 @@ struct Engine {
       const float* h = y.ff.merged + 256; const int ldh = y.ff.fan;      // this layer's input (h, chi) lives inside the
       const float* chi = y.FV + 32; const int ldc = 64;                   // feed-forward GCP's concatenated inputs
       Gcp& m0 = y.msg[0];
-      be.run(E * (512 + d.Ed), FGatherS{rc, h, ldh, EE, d.Ed, m0.merged, m0.fan});
+      if (variant) {        // split form: the endpoint parts of scalar_out are node-level GEMMs, gathered in FScalarOut
+        be.gemm(false, true, N, 256, 256, h, ldh, m0.Ws, m0.fanW, PI, 256, 0.f);
+        be.gemm(false, true, N, 256, 256, h, ldh, m0.Ws + 256 + d.Ed, m0.fanW, PJ, 256, 0.f);
+      } else {
+        be.run(E * (512 + d.Ed), FGatherS{rc, h, ldh, EE, d.Ed, m0.merged, m0.fan});
+      }
       be.run(E * 3 * (64 + d.Xd), FGatherV{rc, chi, ldc, XI, d.Xd, m0.vt});
       gcp_forward(m0, y.msg[1].merged, y.msg[1].fan, nullptr, 0, y.V[0], 32, nullptr, 0, nullptr);
       for (int k = 1; k < 4; ++k) {                                       // residual message GCPs (gcpnet.py:698-701)
@@ -722,41 +790,71 @@ struct Engine {
     const EdgeRc* rc = tp.edge_rc;
     if (grad_count) be.run((long long)grad_count, FFill{grad_base, 0.f});
     be.run(N, FDFinal{tp, d_out, d.F, d.Hin, DX, DHP});
-    gcp_backward(g_proj, DHP, d.Hin, nullptr, 0, DMN, DCHI, 32, 0.f);
-    be.run(N * 256, FCopy2D{DMN, g_proj.fan, DH, 256, 256});
+    if (variant) {
+      gcp_backward(g_proj, DHP, d.Hin, nullptr, 0, out1(DH, 256, 0.f, DCHI, 32, 0.f));
+    } else {
+      gcp_backward(g_proj, DHP, d.Hin, nullptr, 0, out0(DMN, DCHI, 32, 0.f));
+      be.run(N * 256, FCopy2D{DMN, g_proj.fan, DH, 256, 256});
+    }
     if (E) { be.run(E * d.Ed, FFill{DE, 0.f}); be.run(E * 3 * d.Xd, FFill{DXI, 0.f}); }
     for (int l = d.L - 1; l >= 0; --l) {
       Layer& y = layers[l];
-      // x_{l+1} = (x_l + pv) * mask and the frames are frozen: d x is the same masked vector at every layer
-      gcp_backward(y.pos, nullptr, 0, DX, 1, DMN, DFV, 32, 0.f);
-      be.run(N * 256, FMaskAdd{DH, 256, DMN, y.pos.fan, 256, 1, tp.mask});
-      be.run(N * 96, FMaskAdd{DCHI, 32, DFV, 32, 32, 3, tp.mask});
-      gcp_backward(y.ff, DH, 256, DCHI, 32, DMN, DFV, 64, 0.f);
-      // message passing: d agg_s = DMN[:, :256], d agg_v = DFV[:, :32]
       Gcp& m0 = y.msg[0];
+      const float* h = y.ff.merged + 256; const int ldh = y.ff.fan;
+      // x_{l+1} = (x_l + pv) * mask and the frames are frozen: d x is the same masked vector at every layer
+      if (variant) {
+        gcp_backward(y.pos, nullptr, 0, DX, 1, out1(DMN, 256, 0.f, DFV, 32, 0.f));
+        be.run(N * 256, FMaskAdd{DH, 256, DMN, 256, 256, 1, tp.mask});
+      } else {
+        gcp_backward(y.pos, nullptr, 0, DX, 1, out0(DMN, DFV, 32, 0.f));
+        be.run(N * 256, FMaskAdd{DH, 256, DMN, y.pos.fan, 256, 1, tp.mask});
+      }
+      be.run(N * 96, FMaskAdd{DCHI, 32, DFV, 32, 32, 3, tp.mask});
+      // feed-forward GCP: d[agg_s | h] -> DMN[:, :512] (row length ldm), d[agg_v | chi] -> DFV [N*3, 64]
+      const int ldm = variant ? 512 : y.ff.fan;
+      if (variant) gcp_backward(y.ff, DH, 256, DCHI, 32, out1(DMN, 512, 0.f, DFV, 64, 0.f));
+      else gcp_backward(y.ff, DH, 256, DCHI, 32, out0(DMN, DFV, 64, 0.f));
+      // message passing: d agg_s = DMN[:, :256], d agg_v = DFV[:, :32]
       if (E) {
-        be.run(E, FDAttnPre{rc, DMN, y.ff.fan, y.S3, y.attn, DPRE});
+        be.run(E, FDAttnPre{rc, DMN, ldm, y.S3, y.attn, DPRE});
         be.gemm(true, false, 1, 256, E, DPRE, 1, y.S3, 256, y.gwa, 256, 1.f);
         colsum(DPRE, E, 1, 1, y.gba);
-        be.run(E * 256, FDAttnS{rc, DMN, y.ff.fan, y.attn, DPRE, y.wa, DS});
+        be.run(E * 256, FDAttnS{rc, DMN, ldm, y.attn, DPRE, y.wa, DS});
         be.run(E * 96, FGatherRowV{rc, DFV, 64, DV});
         for (int k = 3; k >= 1; --k) {
-          gcp_backward(y.msg[k], DS, 256, DV, 32, DME, DV, 32, 1.f);
-          be.run(E * 256, FAdd2D{DME, y.msg[k].fan, DS, 256, 256});
+          if (variant) {
+            gcp_backward(y.msg[k], DS, 256, DV, 32, out1(DS, 256, 1.f, DV, 32, 1.f));    // residual: += in place
+          } else {
+            gcp_backward(y.msg[k], DS, 256, DV, 32, out0(DME, DV, 32, 1.f));
+            be.run(E * 256, FAdd2D{DME, y.msg[k].fan, DS, 256, 256});
+          }
         }
-        gcp_backward(m0, DS, 256, DV, 32, DME, DMV, 64 + d.Xd, 0.f);
+        if (variant) gcp_backward(m0, DS, 256, DV, 32, out1(nullptr, 0, 0.f, DMV, 64 + d.Xd, 0.f));
+        else gcp_backward(m0, DS, 256, DV, 32, out0(DME, DMV, 64 + d.Xd, 0.f));
       }
-      be.run(N * 256, FAdd2D{DMN + 256, y.ff.fan, DH, 256, 256});
+      be.run(N * 256, FAdd2D{DMN + 256, ldm, DH, 256, 256});
       be.run(N * 96, FAdd2D{DFV + 32, 64, DCHI, 32, 32});
       if (E) {
-        be.run(N * 256, FScatterS{tp, apos, DME, m0.fan, d.Ed, DH, 256});
+        if (variant) {
+          // split message GCP 0: sc.dz is d z0 [E, 256].  e block of the weight, then the node-level endpoint blocks
+          be.gemm(true, false, 256, d.Ed, E, sc.dz, 256, EE, d.Ed, m0.gWs + 256, m0.fanW, 1.f);
+          be.gemm(false, false, E, d.Ed, 256, sc.dz, 256, m0.Ws + 256, m0.fanW, DE, d.Ed, 1.f);
+          be.run(N * 256, FScatterDZ{tp, apos, sc.dz, PI, PJ});        // PI / PJ reused as d PI / d PJ
+          be.gemm(true, false, 256, 256, N, PI, 256, h, ldh, m0.gWs, m0.fanW, 1.f);
+          be.gemm(true, false, 256, 256, N, PJ, 256, h, ldh, m0.gWs + 256 + d.Ed, m0.fanW, 1.f);
+          be.gemm(false, false, N, 256, 256, PI, 256, m0.Ws, m0.fanW, DH, 256, 1.f);
+          be.gemm(false, false, N, 256, 256, PJ, 256, m0.Ws + 256 + d.Ed, m0.fanW, DH, 256, 1.f);
+        } else {
+          be.run(N * 256, FScatterS{tp, apos, DME, m0.fan, d.Ed, DH, 256});
+          be.run(E * d.Ed, FAdd2D{DME + 256, m0.fan, DE, d.Ed, d.Ed});
+        }
         be.run(N * 96, FScatterV{tp, apos, DMV, 64 + d.Xd, d.Xd, DCHI, 32});
-        be.run(E * d.Ed, FAdd2D{DME + 256, m0.fan, DE, d.Ed, d.Ed});
         be.run(E * 3 * d.Xd, FAdd2D{DMV + 32, 64 + d.Xd, DXI, d.Xd, d.Xd});
       }
     }
-    gcp_backward(g_node, DH, 256, DCHI, 32, DMN, nullptr, 0, 0.f);     // embedding inputs are data: no input gradient
-    gcp_backward(g_edge, DE, d.Ed, DXI, d.Xd, DME, nullptr, 0, 0.f);
+    // embedding inputs are data: no input gradient
+    gcp_backward(g_node, DH, 256, DCHI, 32, variant ? out1(nullptr, 0, 0.f, nullptr, 0, 0.f) : out0(DMN, nullptr, 0, 0.f));
+    gcp_backward(g_edge, DE, d.Ed, DXI, d.Xd, variant ? out1(nullptr, 0, 0.f, nullptr, 0, 0.f) : out0(DME, nullptr, 0, 0.f));
   }
 };
 

@@ -251,10 +251,14 @@ BDIFF_API int32_t bdiff_prepare_context(void* stream, const float* props, const 
  *   (the buffer is overwritten, not accumulated into).  No atomics: results are bit-reproducible.
  * bdiff_train_precision: tf32 = 0 (default) fp32 GEMMs, 1 = TF32 tensor-core GEMMs (the reference's bf16-mixed training
  *   configuration is the looser of the two).
+ * bdiff_train_variant: 0 (default) the reference's operator graph one to one; 1 = same mathematics with message GCP 0 in
+ *   split form (node-level h.Wsi^T / h.Wsj^T instead of the [E, 512+Ed] gather + GEMM), activations kept on the tape and
+ *   input gradients written straight into their consumers.  Takes effect at the next bdiff_train_forward.
  * All on `stream`, no host synchronisation.  Errors: BDIFF_ESTATE without a plan / tape, BDIFF_ENOMEM for the tape. */
 BDIFF_API int64_t bdiff_param_floats(const bdiff_handle* h);
 BDIFF_API int32_t bdiff_param_layout(bdiff_handle* h, const char* name, int64_t* offset, int64_t* count);
 BDIFF_API int32_t bdiff_train_precision(bdiff_handle* h, int32_t tf32);
+BDIFF_API int32_t bdiff_train_variant(bdiff_handle* h, int32_t variant);
 BDIFF_API int32_t bdiff_train_forward(bdiff_handle* h, void* stream, const float* params_flat, const float* xh, const float* t,
                                       const float* context, float* net_out);
 BDIFF_API int32_t bdiff_train_backward(bdiff_handle* h, void* stream, const float* d_net_out, float* grads_flat);

@@ -22,8 +22,11 @@ struct HostBackend {
     for (long long i = 0; i < n; ++i) f(i);
   }
   // row-major  C[M,N] = op(A)[M,K] * op(B)[K,N] + beta * C
+  // (the leading-dimension rules of cuBLAS are enforced so that an illegal call fails here, not on the GPU)
+  int bad_ld = 0;
   void gemm(bool ta, bool tb, long long M, int N, long long K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, float beta) {
+    if (lda < (ta ? M : K) || ldb < (tb ? K : N) || ldc < N || lda < 1 || ldb < 1) ++bad_ld;
     for (long long m = 0; m < M; ++m)
       for (int n = 0; n < N; ++n) {
         double acc = 0.0;
@@ -42,7 +45,7 @@ extern "C" int hostcheck_train(const int* dims, int B, int N, long long E, int M
                                const int* act_idx, const long long* edge_off, const int* node_mol, const unsigned char* mask,
                                const int* edge_rc, const char* names, const long long* offsets, int nparams,
                                const float* params, float* grads, long long nfloats, const float* xh, const float* t,
-                               const float* ctx, const float* d_out, float* net_out) {
+                               const float* ctx, const float* d_out, float* net_out, int variant) {
   NetDims d{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5]};
   Topo tp;
   tp.B = B; tp.N = N; tp.E = E; tp.Mact = Mact;
@@ -63,6 +66,7 @@ extern "C" int hostcheck_train(const int* dims, int B, int N, long long E, int M
   };
   HostBackend be;
   Engine<HostBackend> eng(be);
+  eng.variant = variant;
   const size_t need = eng.layout(d, tp, nullptr, look);
   if (missing) return -missing;
   std::vector<float> arena(need, 0.f);
@@ -72,5 +76,5 @@ extern "C" int hostcheck_train(const int* dims, int B, int N, long long E, int M
   eng.grad_count = (size_t)nfloats;
   eng.forward(xh, t, ctx, net_out);
   eng.backward(d_out);
-  return 0;
+  return be.bad_ld ? 1000000 + be.bad_ld : 0;
 }

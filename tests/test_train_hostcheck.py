@@ -51,7 +51,7 @@ def host_plan(bi: torch.Tensor, mask: torch.Tensor):
                 act_idx=act_idx, edge_off=edge_off, node_mol=bi.astype(np.int32), mask=mk, edge_rc=rc)
 
 
-def run_hostcheck(lib, cfg, sd, bi, mask, xh, t, ctx, d_out):
+def run_hostcheck(lib, cfg, sd, bi, mask, xh, t, ctx, d_out, variant=0):
     pl = host_plan(bi, mask)
     names = list(sd.keys())
     offs, tot = [], 0
@@ -75,15 +75,16 @@ def run_hostcheck(lib, cfg, sd, bi, mask, xh, t, ctx, d_out):
                              P(pl["mol_off"]), P(pl["act_off"]), P(pl["act_idx"]), P(pl["edge_off"]), P(pl["node_mol"]),
                              P(pl["mask"]), P(pl["edge_rc"]), C.c_char_p("\n".join(names).encode()), P(offs_),
                              C.c_int(len(names)), P(params), P(grads), C.c_longlong(tot), P(xh_), P(t_), P(ctx_), P(d_),
-                             P(out))
-    assert rc == 0, f"hostcheck_train: {-rc} parameter names not found"
+                             P(out), C.c_int(variant))
+    assert rc == 0, f"hostcheck_train: rc {rc} (<0: parameter names not found; >1e6: GEMM calls with illegal leading dimensions)"
     g = {k: torch.from_numpy(grads[o:o + sd[k].numel()].copy()).reshape(sd[k].shape) for k, o in zip(names, offs)}
     return torch.from_numpy(out), g
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("cname,sizes,masked", [("qm9", [5, 1, 7], [2]), ("qm9_cond", [4, 6], [5]), ("geom", [9, 3, 1], [0, 10]),
                                                 ("geom", [4, 4], [])])
-def test_training_pass_matches_autograd(cname, sizes, masked):
+def test_training_pass_matches_autograd(cname, sizes, masked, variant):
     lib = build_hostcheck()
     cfg = O.config_named(cname)
     sd = O.random_state_dict(cfg, 21, scale=0.7)
@@ -101,7 +102,7 @@ def test_training_pass_matches_autograd(cname, sizes, masked):
     sda = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     out_a = O.denoiser_forward(sda, cfg, bi, mask, xh, t, ctx)
     (out_a * d_out).sum().backward()
-    out_h, grads = run_hostcheck(lib, cfg, sd, bi, mask, xh, t, ctx, d_out)
+    out_h, grads = run_hostcheck(lib, cfg, sd, bi, mask, xh, t, ctx, d_out, variant)
     err_f = (out_h - out_a.detach()).abs().max().item() / out_a.detach().abs().max().item()
     assert err_f < 2e-5, err_f
     worst, worst_key = 0.0, None
