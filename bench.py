@@ -496,7 +496,6 @@ def run_train(args):
     import torch.distributed as dist
     import bdiff
     from bdiff.datasets import GEOM_N_NODES, sample_num_nodes
-    from bdiff.distributed import allreduce_mean_
     from bdiff.optim import GCDMTrainTail
     import gcpnet_oracle as O   # seeded synthetic weights + the CPU baseline leg only
 
@@ -544,8 +543,7 @@ def run_train(args):
         opt.zero_grad()
         loss = tl(*batch, None)[0].mean()
         loss.backward()
-        if world > 1:
-            allreduce_mean_(opt.grads)                           # DDP: mean of the gradients, one bucketed all-reduce
+        opt.allreduce_grads()                                    # DDP: mean of the gradients, ONE all-reduce of the flat buffer
         opt.step()
         return loss.detach()
 
@@ -615,8 +613,7 @@ def run_train(args):
     ev[1].record()
     loss.backward()
     ev[2].record()
-    if world > 1:
-        allreduce_mean_(opt.grads)
+    opt.allreduce_grads()
     ev[3].record()
     opt.step()
     ev[4].record()
@@ -646,7 +643,7 @@ def run_train(args):
                    "objective": "GCDMTrainLoss = reference training-mode L2 objective (t ~ U{0..T}, one denoiser call)",
                    "optimizer": "adaptive gradient-norm clip + AdamW(amsgrad) + EMA 0.9999 (bdiff_optimizer_step)",
                    "l2": "flushed between timed steps (256 MiB write)",
-                   "parallelism": f"dp{world}: one batch per rank, gradients averaged with one bucketed NCCL all-reduce per step"},
+                   "parallelism": f"dp{world}: one batch per rank, gradients averaged with one NCCL all-reduce of the flat gradient buffer per step"},
         "e2e": {"value": mols / secs_e2e, "unit": "molecules/s", "ms_per_step": 1000 * secs_e2e / args.steps,
                 "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in batches[0])), "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches) * world,

@@ -108,6 +108,16 @@ def shard_imbalance(num_nodes: Sequence[int], world_size: int) -> float:
     return max(loads) / mean if mean > 0 else 1.0
 
 
+def allreduce_mean_flat_(flat: torch.Tensor, group=None) -> int:
+    """In-place mean over the ranks of ONE contiguous buffer (GCDMTrainTail keeps all gradients in one): a single
+    all-reduce, no packing.  Returns the number of collectives issued (0 when the world size is 1)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    return 1
+
+
 def allreduce_mean_(tensors: Sequence[torch.Tensor], group=None, bucket_bytes: int = 64 << 20) -> int:
     """In-place mean over the ranks of `group` of every tensor in `tensors` (the gradients of one step), packed into
     contiguous buckets of at most `bucket_bytes` so that a 2.7 M-parameter model is ONE all-reduce.  All tensors must

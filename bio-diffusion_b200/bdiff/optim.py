@@ -45,7 +45,14 @@ class GCDMTrainTail:
         self.hyper = OptHyper(lr, betas[0], betas[1], eps, weight_decay, ema_decay, int(bool(amsgrad)),
                               int(bool(clip_gradients)), int(queue_len))
         z = lambda p: torch.zeros_like(p)
-        self.grads = [z(p) for p in self.params]
+        # all gradients in ONE flat buffer (each tensor at a multiple of 64 floats): zero_grad is one memset and the DDP
+        # exchange one all-reduce of the buffer itself, no packing
+        offs, tot = [], 0
+        for p in self.params:
+            offs.append(tot)
+            tot += (p.numel() + 63) // 64 * 64
+        self.grad_flat = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.grads = [self.grad_flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
         self.exp_avg = [z(p) for p in self.params]
         self.exp_avg_sq = [z(p) for p in self.params]
         self.max_exp_avg_sq = [z(p) for p in self.params] if amsgrad else None
@@ -79,8 +86,13 @@ class GCDMTrainTail:
         self.partial = torch.zeros(len(ct), dtype=torch.float64, device=dev)
 
     def zero_grad(self):
-        for g in self.grads:
-            g.zero_()
+        self.grad_flat.zero_()
+
+    def allreduce_grads(self, group=None) -> int:
+        """DDP gradient exchange (configs/trainer/ddp.yaml): in-place mean over the ranks of the flat gradient buffer, ONE
+        NCCL all-reduce.  Returns the number of collectives issued (0 on a single rank)."""
+        from .distributed import allreduce_mean_flat_
+        return allreduce_mean_flat_(self.grad_flat, group)
 
     def step(self):
         for p, g in zip(self.params, self.grads):

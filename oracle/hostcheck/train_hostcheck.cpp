@@ -18,7 +18,8 @@ using namespace bdiff::train;
 namespace {
 struct HostBackend {
   template <class F>
-  void run(long long n, const F& f) {
+  void run(long long n, const F& f) {      // every functor writes only its own output elements: any order / parallelism is valid
+#pragma omp parallel for schedule(static)
     for (long long i = 0; i < n; ++i) f(i);
   }
   // row-major  C[M,N] = op(A)[M,K] * op(B)[K,N] + beta * C
@@ -27,6 +28,7 @@ struct HostBackend {
   void gemm(bool ta, bool tb, long long M, int N, long long K, const float* A, int lda, const float* B, int ldb, float* C,
             int ldc, float beta) {
     if (lda < (ta ? M : K) || ldb < (tb ? K : N) || ldc < N || lda < 1 || ldb < 1) ++bad_ld;
+#pragma omp parallel for collapse(2) schedule(static)
     for (long long m = 0; m < M; ++m)
       for (int n = 0; n < N; ++n) {
         double acc = 0.0;

@@ -68,7 +68,7 @@ def _grad_worker(rank, world, port, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from bdiff.distributed import allreduce_mean_
+    from bdiff.distributed import allreduce_mean_, allreduce_mean_flat_
     g = torch.Generator().manual_seed(100 + rank)
     shapes = [(256, 605), (256,), (32, 8), (1, 256), (17,)]
     grads = [torch.randn(s, generator=g) for s in shapes]
@@ -76,7 +76,13 @@ def _grad_worker(rank, world, port, results):
     n_one = allreduce_mean_(grads)                       # everything in one bucket
     again = [t.clone() for t in mine]
     n_many = allreduce_mean_(again, bucket_bytes=4096)   # forced into several buckets: same result
-    results[rank] = (mine, grads, again, n_one, n_many)
+    flat = torch.cat([t.reshape(-1) for t in mine])       # the optimiser tail's layout: views of one buffer
+    views, o = [], 0
+    for t in mine:
+        views.append(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
+    n_flat = allreduce_mean_flat_(flat)
+    results[rank] = (mine, grads, again, n_one, n_many, [v.clone() for v in views], n_flat)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -86,12 +92,13 @@ def test_two_rank_gradient_allreduce_mean():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_grad_worker, args=(2, 29533, results), nprocs=2, join=True)
-    (a0, r0, m0, n_one0, n_many0), (a1, r1, m1, n_one1, n_many1) = results[0], results[1]
-    assert n_one0 == n_one1 == 1 and n_many0 == n_many1 and n_many0 > 1
-    for x0, x1, y0, y1, z0 in zip(a0, a1, r0, r1, m0):
+    (a0, r0, m0, n_one0, n_many0, f0, nf0), (a1, r1, m1, n_one1, n_many1, f1, nf1) = results[0], results[1]
+    assert n_one0 == n_one1 == 1 and n_many0 == n_many1 and n_many0 > 1 and nf0 == nf1 == 1
+    for x0, x1, y0, y1, z0, v0, v1 in zip(a0, a1, r0, r1, m0, f0, f1):
         want = (x0 + x1) / 2
         assert torch.allclose(y0, want, rtol=0, atol=1e-7) and torch.equal(y0, y1)
         assert torch.allclose(z0, want, rtol=0, atol=1e-7)
+        assert torch.equal(v0, y0) and torch.equal(v0, v1)          # flat-buffer exchange == bucketed exchange
 
 
 def test_allreduce_mean_single_process_is_noop():

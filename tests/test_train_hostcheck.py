@@ -22,7 +22,7 @@ HDR = os.path.join(ROOT, "bio-diffusion_b200", "csrc", "bdiff_train_engine.cuh")
 def build_hostcheck():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", OUT, SRC])
+        subprocess.check_call(["g++", "-O2", "-fopenmp", "-std=c++17", "-shared", "-fPIC", "-o", OUT, SRC])
     return C.CDLL(OUT)
 
 
@@ -83,7 +83,7 @@ def run_hostcheck(lib, cfg, sd, bi, mask, xh, t, ctx, d_out, variant=0):
 
 @pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("cname,sizes,masked", [("qm9", [5, 1, 7], [2]), ("qm9_cond", [4, 6], [5]), ("geom", [9, 3, 1], [0, 10]),
-                                                ("geom", [4, 4], [])])
+                                                ("geom", [4, 4], []), ("geom", [131, 2], [7])])
 def test_training_pass_matches_autograd(cname, sizes, masked, variant):
     lib = build_hostcheck()
     cfg = O.config_named(cname)
