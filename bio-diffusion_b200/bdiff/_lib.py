@@ -64,6 +64,7 @@ PROTOTYPES = {
     "bdiff_param_layout": (C.c_int32, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "bdiff_train_precision": (C.c_int32, [C.c_void_p, C.c_int32]),
     "bdiff_train_variant": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "bdiff_train_timing": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]),
     "bdiff_train_forward": (C.c_int32, [C.c_void_p] * 7),
     "bdiff_train_backward": (C.c_int32, [C.c_void_p] * 4),
     "bdiff_nan_guard_count": (C.c_int32, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),

@@ -329,8 +329,8 @@ class GCPNetDynamicsB200(nn.Module):
         return _DenoiseTrainFn.apply(self, batch_index, mask, xh, t, context, num_mols, *self.parameters())
 
     def set_train_variant(self, variant: int) -> None:
-        """0: the reference's operator graph one to one; 1: split message GCP 0 + tape-resident activations (same
-        mathematics, fewer FLOPs and bytes).  Takes effect at the next training forward."""
+        """1 (default): split message GCP 0 + tape-resident activations; 0: the reference's operator graph one to one (same
+        mathematics, more FLOPs and bytes; the cross-check).  Takes effect at the next training forward."""
         lib = _lib.load()
         _lib.check(self._ensure_handle(), lib.bdiff_train_variant(self._ensure_handle(), int(variant)), "bdiff_train_variant")
 

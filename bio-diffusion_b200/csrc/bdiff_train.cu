@@ -4,6 +4,12 @@
 // layout; fp32 by default, TF32 tensor cores on request).  Everything runs on the caller's stream, no host
 // synchronisation, no atomics: gradients are bit-reproducible from run to run.
 #include <cublas_v2.h>
+#include <cxxabi.h>
+
+#include <algorithm>
+#include <typeinfo>
+
+#include <cstring>
 
 #include "bdiff_handle.h"
 #include "bdiff_train_engine.cuh"
@@ -16,15 +22,52 @@ __global__ void __launch_bounds__(256) k_train(long long n, F f) {
   if (i < n) f(i);
 }
 
+// Optional per-operation timing (bdiff_train_timing): a CUDA event pair around every kernel / GEMM on the launch stream.
+struct OpTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  std::vector<std::pair<std::string, size_t>> recs;     // (operation, index of its first event)
+  long long E = 0, N = 0;                              // to print GEMM shapes symbolically
+  cudaEvent_t next() {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  std::string dim(long long x) const {
+    if (E > 0 && x == E) return "E";
+    if (E > 0 && x == 3 * E) return "3E";
+    if (N > 0 && x == N) return "N";
+    if (N > 0 && x == 3 * N) return "3N";
+    return std::to_string(x);
+  }
+};
+
 struct CudaBackend {
   cudaStream_t st = nullptr;
   cublasHandle_t cb = nullptr;
   cublasStatus_t blas_err = CUBLAS_STATUS_SUCCESS;
   int64_t launches = 0, gemms = 0;
+  OpTimer tm;
   template <class F>
   void run(long long n, const F& f) {
     if (n <= 0) return;
+    cudaEvent_t e1 = nullptr;
+    if (tm.on) {
+      int status = 0;
+      char* dn = abi::__cxa_demangle(typeid(F).name(), nullptr, nullptr, &status);
+      std::string name = (status == 0 && dn) ? dn : typeid(F).name();
+      if (dn) free(dn);
+      const size_t pos = name.rfind("::");
+      tm.recs.emplace_back("k_train<" + (pos == std::string::npos ? name : name.substr(pos + 2)) + ">", tm.used);
+      cudaEventRecord(tm.next(), st);
+      e1 = tm.next();
+    }
     k_train<F><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
+    if (e1) cudaEventRecord(e1, st);
     ++launches;
   }
   // row-major C[M,N] = op(A)[M,K] * op(B)[K,N] + beta*C  ==  column-major C^T[N,M] = op(B)^T * op(A)^T
@@ -32,8 +75,16 @@ struct CudaBackend {
             int ldc, float beta) {
     if (M <= 0 || N <= 0 || K <= 0) return;
     const float alpha = 1.0f;
+    cudaEvent_t e1 = nullptr;
+    if (tm.on) {
+      tm.recs.emplace_back(std::string("cublasSgemm ") + (ta ? "T" : "N") + (tb ? "T" : "N") + " m=" + tm.dim(M) + " n=" +
+                           std::to_string(N) + " k=" + tm.dim(K), tm.used);
+      cudaEventRecord(tm.next(), st);
+      e1 = tm.next();
+    }
     cublasStatus_t s = cublasSgemm(cb, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, N, (int)M, (int)K, &alpha,
                                    B, ldb, A, lda, &beta, C, ldc);
+    if (e1) cudaEventRecord(e1, st);
     if (s != CUBLAS_STATUS_SUCCESS && blas_err == CUBLAS_STATUS_SUCCESS) blas_err = s;
     ++gemms;
   }
@@ -48,11 +99,12 @@ struct TrainState {
   const float* params = nullptr;
   float* grads = nullptr;
   bool tf32 = false;
-  int variant = 0, laid_variant = -1;
+  int variant = 1, laid_variant = -1;    // 1 = split message GCP 0 (default since it was validated on the device); 0 = plain graph
 };
 
 void train_destroy(TrainState* t) {
   if (!t) return;
+  for (cudaEvent_t e : t->be.tm.ev) cudaEventDestroy(e);
   if (t->be.cb) cublasDestroy(t->be.cb);
   t->arena.release();
   delete t;
@@ -143,6 +195,54 @@ int32_t bdiff_train_precision(bdiff_handle* h, int32_t tf32) {
   if (!h->train) h->train = new TrainState();
   h->train->tf32 = tf32 != 0;
   if (h->train->be.cb) cublasSetMathMode(h->train->be.cb, tf32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_DEFAULT_MATH);
+  return BDIFF_OK;
+}
+
+int32_t bdiff_train_timing(bdiff_handle* h, void* stream, int32_t enable, char* report, int64_t report_bytes) {
+  if (!h) return BDIFF_EINVAL;
+  if (!h->train) h->train = new TrainState();
+  OpTimer& tm = h->train->be.tm;
+  if (enable) {
+    tm.on = true;
+    tm.used = 0;
+    tm.recs.clear();
+    tm.E = h->have_plan ? h->plan.E : 0;
+    tm.N = h->have_plan ? h->plan.N : 0;
+    return BDIFF_OK;
+  }
+  tm.on = false;
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return h->fail(BDIFF_ECUDA, "train_timing: %s", cudaGetErrorString(e));
+  std::map<std::string, std::pair<int, double>> agg;
+  double total = 0.0;
+  for (auto& r : tm.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, tm.ev[r.second], tm.ev[r.second + 1]) != cudaSuccess) continue;
+    auto& a = agg[r.first];
+    a.first += 1;
+    a.second += ms;
+    total += ms;
+  }
+  std::vector<std::pair<std::string, std::pair<int, double>>> rows(agg.begin(), agg.end());
+  std::sort(rows.begin(), rows.end(), [](const auto& a, const auto& b) { return a.second.second > b.second.second; });
+  std::string out;
+  char line[256];
+  snprintf(line, sizeof line, "%-44s %6s %10s %8s\n", "operation (E=%lld edges, N=%lld nodes)", "calls", "total_ms", "share");
+  char hdr[256];
+  snprintf(hdr, sizeof hdr, line, tm.E, tm.N);
+  out += hdr;
+  for (auto& r : rows) {
+    snprintf(line, sizeof line, "%-44s %6d %10.3f %7.1f%%\n", r.first.c_str(), r.second.first, r.second.second,
+             total > 0 ? 100.0 * r.second.second / total : 0.0);
+    out += line;
+  }
+  snprintf(line, sizeof line, "%-44s %6zu %10.3f\n", "sum of the per-operation times", tm.recs.size(), total);
+  out += line;
+  if (report && report_bytes > 0) {
+    const size_t n = std::min<size_t>(out.size(), (size_t)report_bytes - 1);
+    memcpy(report, out.data(), n);
+    report[n] = 0;
+  }
   return BDIFF_OK;
 }
 
